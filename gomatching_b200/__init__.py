@@ -1,0 +1,46 @@
+"""gomatching_b200 -- B200-native (sm_100a) multi-scale deformable attention for GoMatching / DeepSolo.
+
+Public surface (mirrors third_party/adet/layers/ms_deform_attn.py of the reference):
+    MSDeformAttn                 nn.Module drop-in
+    MSDeformAttnFunction         autograd Function drop-in (alias _MSDeformAttnFunction)
+    ms_deform_attn_forward       adet._C.ms_deform_attn_forward drop-in
+    ms_deform_attn_backward      adet._C.ms_deform_attn_backward drop-in
+    ms_deform_attn_forward_fused softmax + offsets->locations + sampler in one kernel
+    install_into_adet            monkey-patch the reference's import sites
+"""
+from .ms_deform_attn_func import (MSDeformAttnFunction, _MSDeformAttnFunction, fused_supported, locations_softmax,
+                                  ms_deform_attn_backward, ms_deform_attn_forward, ms_deform_attn_forward_fused,
+                                  sample_index)
+from .ms_deform_attn import MSDeformAttn
+
+__all__ = [
+    "MSDeformAttn", "MSDeformAttnFunction", "_MSDeformAttnFunction", "ms_deform_attn_forward",
+    "ms_deform_attn_backward", "ms_deform_attn_forward_fused", "fused_supported", "sample_index",
+    "locations_softmax", "install_into_adet",
+]
+
+
+def install_into_adet():
+    """Bind this implementation where the reference looks its operator up.
+
+    * ``adet._C.ms_deform_attn_forward/backward``  (csrc/vision.cpp:52-55) -> the C-ABI kernels
+    * ``adet.layers.ms_deform_attn.MSDeformAttn`` and ``adet.layers.deformable_transformer.MSDeformAttn``
+      (deformable_transformer.py:16) -> :class:`MSDeformAttn`
+    Call after ``adet`` is importable; modules that are not imported yet are skipped.
+    """
+    import sys
+    import types
+
+    c = sys.modules.get("adet._C")
+    if c is None:
+        c = types.ModuleType("adet._C")
+        sys.modules["adet._C"] = c
+        if "adet" in sys.modules:
+            sys.modules["adet"]._C = c
+    c.ms_deform_attn_forward = ms_deform_attn_forward
+    c.ms_deform_attn_backward = ms_deform_attn_backward
+    for name in ("adet.layers.ms_deform_attn", "adet.layers.deformable_transformer", "adet.layers"):
+        mod = sys.modules.get(name)
+        if mod is not None and hasattr(mod, "MSDeformAttn"):
+            mod.MSDeformAttn = MSDeformAttn
+    return c

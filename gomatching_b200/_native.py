@@ -1,0 +1,119 @@
+"""ctypes binding of libmsda_b200.so (include/msda_b200.h).  No fallback: if the library is missing or a
+call fails, this raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmsda_b200.so")
+_lock = threading.Lock()
+_lib = None
+
+# every symbol include/msda_b200.h declares; tests/test_abi.py checks header <-> list <-> .so agree
+SYMBOLS = (
+    "msda_b200_abi_version",
+    "msda_b200_error_string",
+    "msda_b200_sm_count",
+    "msda_b200_variant_count",
+    "msda_b200_forward_f32",
+    "msda_b200_forward_bf16",
+    "msda_b200_forward_f32_ex",
+    "msda_b200_forward_bf16_ex",
+    "msda_b200_forward_fused_f32",
+    "msda_b200_forward_fused_bf16",
+    "msda_b200_locations_softmax_f32",
+    "msda_b200_sample_index_f32",
+    "msda_b200_backward_f32",
+    "msda_b200_host_ctx_create",
+    "msda_b200_host_ctx_destroy",
+    "msda_b200_forward_f32_host",
+)
+
+
+class Tuning(ctypes.Structure):
+    """msda_b200_tuning_t"""
+    _fields_ = [
+        ("mode", ctypes.c_int32),
+        ("tile_h", ctypes.c_int32),
+        ("tile_w", ctypes.c_int32),
+        ("tile_q", ctypes.c_int32),
+        ("ctas_per_sm", ctypes.c_int32),
+        ("variant", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 2),
+    ]
+
+
+MODE_AUTO, MODE_LINEAR, MODE_PYRAMID, MODE_GENERIC = 0, 1, 2, 3
+
+
+class MSDAError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library.  Builds it first if nvcc is available and the .so is stale or absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH) or os.environ.get("MSDA_B200_REBUILD") == "1":
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise MSDAError("libmsda_b200.so is missing and could not be built; there is no CPU/PyTorch fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.msda_b200_abi_version.restype = ci
+        L.msda_b200_error_string.restype = ctypes.c_char_p
+        L.msda_b200_error_string.argtypes = [ci]
+        L.msda_b200_sm_count.restype = ci
+        L.msda_b200_variant_count.restype = ci
+        core = [vp, vp, vp, vp, vp] + [ci] * 7 + [vp, vp]
+        for name in ("msda_b200_forward_f32", "msda_b200_forward_bf16"):
+            getattr(L, name).restype = ci
+            getattr(L, name).argtypes = core
+        for name in ("msda_b200_forward_f32_ex", "msda_b200_forward_bf16_ex"):
+            getattr(L, name).restype = ci
+            getattr(L, name).argtypes = core + [ctypes.POINTER(Tuning)]
+        fused = [vp, vp, vp, vp, ci, vp, vp] + [ci] * 7 + [vp, vp, ctypes.POINTER(Tuning)]
+        for name in ("msda_b200_forward_fused_f32", "msda_b200_forward_fused_bf16"):
+            getattr(L, name).restype = ci
+            getattr(L, name).argtypes = fused
+        L.msda_b200_locations_softmax_f32.restype = ci
+        L.msda_b200_locations_softmax_f32.argtypes = [vp, vp, ci, vp, vp] + [ci] * 6 + [vp, vp, vp]
+        L.msda_b200_sample_index_f32.restype = ci
+        L.msda_b200_sample_index_f32.argtypes = [vp, vp, vp] + [ci] * 6 + [vp, vp]
+        L.msda_b200_backward_f32.restype = ci
+        L.msda_b200_backward_f32.argtypes = [vp] * 6 + [ci] * 7 + [vp, vp, vp, vp]
+        L.msda_b200_host_ctx_create.restype = ci
+        L.msda_b200_host_ctx_create.argtypes = [ctypes.POINTER(vp), ci]
+        L.msda_b200_host_ctx_destroy.restype = None
+        L.msda_b200_host_ctx_destroy.argtypes = [vp]
+        L.msda_b200_forward_f32_host.restype = ci
+        L.msda_b200_forward_f32_host.argtypes = [vp] * 6 + [ci] * 7 + [vp]
+        if L.msda_b200_abi_version() != 1:
+            raise MSDAError("libmsda_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "msda_b200") -> None:
+    if rc != 0:
+        msg = lib().msda_b200_error_string(int(rc))
+        raise MSDAError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def make_tuning(tuning) -> "ctypes.POINTER(Tuning) | None":
+    """dict / Tuning / None -> pointer usable in the *_ex calls"""
+    if tuning is None:
+        return None
+    if isinstance(tuning, Tuning):
+        return ctypes.pointer(tuning)
+    t = Tuning()
+    for k, v in dict(tuning).items():
+        setattr(t, k, int(v))
+    return ctypes.pointer(t)

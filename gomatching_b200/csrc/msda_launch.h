@@ -1,0 +1,48 @@
+// Internal launch interface between the C-ABI layer (msda_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msda {
+
+enum TileMode { kModeLinear = 1, kModePyramid = 2, kModeGeneric = 3 };
+
+struct FwdParams {
+  const void* value;          // (N,S,M,D) fp32 or bf16
+  const int64_t* shapes;      // (L,2) device
+  const int64_t* lsi;         // (L,)  device
+  // core operator inputs
+  const float* loc;           // (N,Lq,M,L,P,2)
+  const float* attn;          // (N,Lq,M,L,P)
+  // fused operator inputs (loc/attn == nullptr)
+  const float* ref;           // (N,Lq,L,ref_dim)
+  const float* offsets;       // (N,Lq,M,L,P,2)
+  const float* logits;        // (N,Lq,M,L*P)
+  int ref_dim;
+  void* out;                  // (N,Lq,M*D)
+  int N, S, M, D, L, Lq, P;
+  // tiling (never changes results)
+  int mode;                   // TileMode
+  int tile_q;                 // queries per tile (linear) = tile_h*tile_w (pyramid)
+  int tile_h, tile_w_log2;    // pyramid tile
+  int grid;                   // CTAs to launch
+  int variant;                // kernel instantiation
+};
+
+// Each returns a cudaError_t cast to int (0 = ok) or MSDA_E_UNSUPPORTED (-5).
+int launch_forward_f32(const FwdParams& p, cudaStream_t stream);
+int launch_forward_bf16(const FwdParams& p, cudaStream_t stream);
+int forward_variant_count();
+// true if the tiled kernels can run this problem (else only the generic kernel can)
+bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused);
+
+int launch_sample_index(const float* loc, const int64_t* shapes, const int64_t* lsi, int N, int Lq, int M, int D,
+                        int L, int P, void* out_records, cudaStream_t stream);
+int launch_locations_softmax(const int64_t* shapes, const float* ref, int ref_dim, const float* offsets,
+                             const float* logits, int N, int M, int L, int Lq, int P, int lanes_per_unit,
+                             float* loc_out, float* attn_out, cudaStream_t stream);
+int launch_backward_f32(const float* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
+                        const float* attn, const float* grad_out, int N, int S, int M, int D, int L, int Lq, int P,
+                        float* grad_value, float* grad_loc, float* grad_attn, cudaStream_t stream);
+
+}  // namespace msda

@@ -1,0 +1,125 @@
+"""`MSDeformAttn` -- drop-in for third_party/adet/layers/ms_deform_attn.py:63-156.
+
+Same constructor, same parameter names and shapes (``sampling_offsets``, ``attention_weights``,
+``value_proj``, ``output_proj`` -- DeepSolo / Deformable-DETR checkpoints load unchanged), same
+initialisation (:99-115), same ``forward`` signature and errors.  The core runs on the hand-written
+sm_100a kernels through the C ABI; the four dense projections stay ``nn.Linear`` (cuBLAS tensor-core
+GEMMs -- they border the op, they are not it).
+
+Inference (no autograd): softmax, offset->location and sampling run as ONE fused kernel, so
+``sampling_locations`` / ``attention_weights`` are never written to HBM.  With autograd the reference's
+eager glue + ``MSDeformAttnFunction`` path is used so gradients flow exactly as in the reference.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.init import constant_, xavier_uniform_
+
+from .ms_deform_attn_func import (MSDeformAttnFunction, fused_supported, ms_deform_attn_forward_fused)
+
+
+def _is_power_of_2(n):
+    if (not isinstance(n, int)) or (n < 0):
+        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
+    return (n & (n - 1) == 0) and n != 0
+
+
+class MSDeformAttn(nn.Module):
+    # The reference asserts sum(H*W) == Len_in on a CUDA tensor (ms_deform_attn.py:131): a device->host sync on
+    # every call, 12 per frame.  Off by default; set True to get the reference's AssertionError behaviour.
+    strict_shape_check = False
+
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
+        _d_per_head = d_model // n_heads
+        if not _is_power_of_2(_d_per_head):
+            warnings.warn("You'd better set d_model in MSDeformAttn to make the dimension of each attention head a "
+                          "power of 2 which is more efficient in our CUDA implementation.")
+        self.im2col_step = 64
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+        self.use_fused = True      # fused glue+sampler kernel when no gradient is needed
+        self.tuning = None         # optional msda_b200_tuning_t fields (dict); never changes results
+
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # ms_deform_attn.py:99-115: offsets start on a k-pixel compass rose, attention uniform
+        constant_(self.sampling_offsets.weight.data, 0.)
+        thetas = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        grid_init = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(self.n_heads, 1, 1, 2).repeat(
+            1, self.n_levels, self.n_points, 1)
+        for i in range(self.n_points):
+            grid_init[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(grid_init.view(-1))
+        constant_(self.attention_weights.weight.data, 0.)
+        constant_(self.attention_weights.bias.data, 0.)
+        xavier_uniform_(self.value_proj.weight.data)
+        constant_(self.value_proj.bias.data, 0.)
+        xavier_uniform_(self.output_proj.weight.data)
+        constant_(self.output_proj.bias.data, 0.)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        """
+        :param query                       (N, Length_{query}, C)
+        :param reference_points            (N, Length_{query}, n_levels, 2) in [0, 1], or (..., 4) reference boxes
+        :param input_flatten               (N, sum_l H_l*W_l, C)
+        :param input_spatial_shapes        (n_levels, 2) int64 [(H_0, W_0), ...]
+        :param input_level_start_index     (n_levels,) int64
+        :param input_padding_mask          (N, sum_l H_l*W_l) bool, True for padding
+        :return output                     (N, Length_{query}, C)
+        """
+        N, Len_q, _ = query.shape
+        N, Len_in, _ = input_flatten.shape
+        if self.strict_shape_check:
+            assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
+                reference_points.shape[-1]))
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        D = self.d_model // M
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, Len_in, M, D)
+        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
+        attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
+
+        needs_grad = torch.is_grad_enabled() and (value.requires_grad or sampling_offsets.requires_grad
+                                                  or attention_weights.requires_grad or reference_points.requires_grad)
+        if (self.use_fused and not needs_grad and value.is_cuda and value.dtype in (torch.float32, torch.bfloat16)
+                and fused_supported(value.dtype, D, L, P)):
+            output = ms_deform_attn_forward_fused(
+                value.contiguous(), input_spatial_shapes, input_level_start_index,
+                reference_points.float().contiguous(), sampling_offsets.float().contiguous(),
+                attention_weights.float().contiguous(), tuning=self.tuning)
+        else:
+            attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
+            if reference_points.shape[-1] == 2:
+                offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
+                sampling_locations = reference_points[:, :, None, :, None, :] \
+                    + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+            else:
+                sampling_locations = reference_points[:, :, None, :, None, :2] \
+                    + sampling_offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5
+            output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
+                                                sampling_locations.contiguous(), attention_weights.contiguous(),
+                                                self.im2col_step)
+        return self.output_proj(output)

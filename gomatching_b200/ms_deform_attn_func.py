@@ -1,0 +1,211 @@
+"""Operator layer: drop-in for the reference's `adet._C` entry points and `_MSDeformAttnFunction`.
+
+Reference interfaces mirrored (all under /root/reference/third_party/adet/layers/):
+  * ``_C.ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+    im2col_step)``  -- csrc/vision.cpp:52-53, csrc/DeformAttn/ms_deform_attn.h:20-39,
+    csrc/DeformAttn/ms_deform_attn_cuda.cu:20-80
+  * ``_C.ms_deform_attn_backward(..., grad_output, im2col_step)`` -- csrc/vision.cpp:54-55,
+    ms_deform_attn_cuda.cu:83-153
+  * ``_MSDeformAttnFunction`` -- ms_deform_attn.py:20-37 (same positional arguments, same returned grads)
+
+Differences, none of which change results: the output is allocated uninitialised (the kernels write
+every element once; the reference memsets, ms_deform_attn_cuda.cu:54), all N batch items go in one launch
+(``im2col_step`` only keeps its divisibility check), bf16 value is accepted (the reference dispatches
+fp32/fp64 only, ms_deform_attn_cuda.cu:64).  CPU tensors raise, like the reference
+(ms_deform_attn.h:38 "Not implemented on the CPU") -- there is no CPU or PyTorch fallback here.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _native
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    # ms_deform_attn.h:28-38 / ms_deform_attn_cuda.cu:28-38
+    _require(value.is_cuda, "Not implemented on the CPU")
+    _require(value.is_contiguous(), "value tensor has to be contiguous")
+    _require(spatial_shapes.is_contiguous(), "spatial_shapes tensor has to be contiguous")
+    _require(level_start_index.is_contiguous(), "level_start_index tensor has to be contiguous")
+    _require(sampling_loc.is_contiguous(), "sampling_loc tensor has to be contiguous")
+    _require(attn_weight.is_contiguous(), "attn_weight tensor has to be contiguous")
+    _require(spatial_shapes.is_cuda, "spatial_shapes must be a CUDA tensor")
+    _require(level_start_index.is_cuda, "level_start_index must be a CUDA tensor")
+    _require(sampling_loc.is_cuda, "sampling_loc must be a CUDA tensor")
+    _require(attn_weight.is_cuda, "attn_weight must be a CUDA tensor")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes / level_start_index must be int64")
+    _require(value.dim() == 4 and sampling_loc.dim() == 6 and attn_weight.dim() == 5, "bad tensor ranks")
+    N, S, M, D = value.shape
+    N2, Lq, M2, L, P, two = sampling_loc.shape
+    _require((N2, M2, two) == (N, M, 2), "sampling_loc shape does not match value")
+    _require(tuple(attn_weight.shape) == (N, Lq, M, L, P), "attn_weight shape does not match sampling_loc")
+    _require(spatial_shapes.shape == (L, 2) and level_start_index.shape == (L,), "bad spatial_shapes / level_start_index")
+    return N, S, M, D, L, Lq, P
+
+
+def _check_im2col_step(N: int, im2col_step: int) -> None:
+    step = min(N, int(im2col_step))                        # ms_deform_attn_cuda.cu:50
+    _require(step > 0 and N % step == 0, "batch(%d) must divide im2col_step(%d)" % (N, step))   # :52
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64,
+                           tuning=None):
+    """Same call as ``adet._C.ms_deform_attn_forward``; returns (N, Lq, M*D)."""
+    N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    _check_im2col_step(N, im2col_step)
+    lib = _native.lib()
+    if value.dtype == torch.float32:
+        fn = lib.msda_b200_forward_f32_ex
+    elif value.dtype == torch.bfloat16:
+        fn = lib.msda_b200_forward_bf16_ex
+    else:
+        raise RuntimeError("msda_b200: value dtype %s has no kernel (float32 and bfloat16 are implemented)" % value.dtype)
+    loc = sampling_loc if sampling_loc.dtype == torch.float32 else sampling_loc.float()
+    attn = attn_weight if attn_weight.dtype == torch.float32 else attn_weight.float()
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), loc.data_ptr(),
+                attn.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(), stream, _native.make_tuning(tuning))
+    _native.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                 attention_logits, n_points=None, tuning=None):
+    """softmax(logits) + offsets->locations + sampling + weighted reduction in one kernel.
+
+    value (N,S,M,D) fp32|bf16; reference_points (N,Lq,L,2|4) fp32; sampling_offsets (N,Lq,M,L,P,2) fp32 (raw
+    projection output); attention_logits (N,Lq,M,L*P) fp32 (pre-softmax).  Equivalent to
+    ms_deform_attn.py:137-152 without materialising sampling_locations / attention_weights.
+    """
+    _require(value.is_cuda, "Not implemented on the CPU")
+    for t, name in ((value, "value"), (reference_points, "reference_points"), (sampling_offsets, "sampling_offsets"),
+                    (attention_logits, "attention_logits"), (spatial_shapes, "spatial_shapes"),
+                    (level_start_index, "level_start_index")):
+        _require(t.is_cuda and t.is_contiguous(), "%s tensor has to be a contiguous CUDA tensor" % name)
+    N, S, M, D = value.shape
+    N2, Lq, M2, L, P, two = sampling_offsets.shape
+    _require((N2, M2, two) == (N, M, 2), "sampling_offsets shape does not match value")
+    ref_dim = reference_points.shape[-1]
+    if ref_dim not in (2, 4):
+        raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(ref_dim))
+    _require(tuple(reference_points.shape) == (N, Lq, L, ref_dim), "bad reference_points shape")
+    _require(attention_logits.numel() == N * Lq * M * L * P, "bad attention_logits shape")
+    _require(reference_points.dtype == torch.float32 and sampling_offsets.dtype == torch.float32
+             and attention_logits.dtype == torch.float32, "reference_points / offsets / logits must be float32")
+    lib = _native.lib()
+    if value.dtype == torch.float32:
+        fn = lib.msda_b200_forward_fused_f32
+    elif value.dtype == torch.bfloat16:
+        fn = lib.msda_b200_forward_fused_bf16
+    else:
+        raise RuntimeError("msda_b200: value dtype %s has no kernel" % value.dtype)
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
+                ref_dim, sampling_offsets.data_ptr(), attention_logits.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(),
+                stream, _native.make_tuning(tuning))
+    _native.check(rc, "ms_deform_attn_forward_fused")
+    return out
+
+
+def fused_supported(value_dtype, D: int, L: int, P: int) -> bool:
+    """Shapes the fused kernel is instantiated for (csrc/msda_forward.cu tiled_supported)."""
+    if value_dtype not in (torch.float32, torch.bfloat16) or L > 16:
+        return False
+    if D == 32:
+        return L * P in (8, 16, 32) and (L * P) % (D * value_dtype.itemsize // 16) == 0
+    if D == 64:
+        return L * P == 16
+    return False
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step=64):
+    """Same call as ``adet._C.ms_deform_attn_backward``; returns [grad_value, grad_sampling_loc, grad_attn_weight]."""
+    N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    _require(grad_output.is_cuda, "grad_output must be a CUDA tensor")
+    _check_im2col_step(N, im2col_step)
+    _require(value.dtype == torch.float32, "msda_b200 backward is implemented for float32")
+    grad_output = grad_output.contiguous()
+    grad_value = torch.zeros_like(value)                   # accumulated with atomics, like ms_deform_attn_cuda.cu:118
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _native.lib().msda_b200_backward_f32(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            attn_weight.data_ptr(), grad_output.data_ptr(), N, S, M, D, L, Lq, P, grad_value.data_ptr(),
+            grad_loc.data_ptr(), grad_attn.data_ptr(), stream)
+    _native.check(rc, "ms_deform_attn_backward")
+    return [grad_value, grad_loc, grad_attn]
+
+
+class MSDeformAttnFunction(torch.autograd.Function):
+    """ms_deform_attn.py:20-37, same positional arguments."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                        attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, loc, attn = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = ms_deform_attn_backward(value, shapes, lsi, loc, attn, grad_output,
+                                                                  ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None
+
+
+_MSDeformAttnFunction = MSDeformAttnFunction   # the reference's private name (ms_deform_attn.py:20)
+
+
+def sample_index(sampling_loc, spatial_shapes, level_start_index, n_heads: int, d_head: int):
+    """Dump the sampling indices the kernels derive (same device function): int64 tensor (N,Lq,M,L,P,6) viewed as
+    [h_low, w_low, in_range, corner_mask, level_offset_lo, level_offset_hi] int32 -> returned as a dict of tensors."""
+    _require(sampling_loc.is_cuda and sampling_loc.is_contiguous() and sampling_loc.dtype == torch.float32,
+             "sampling_loc must be a contiguous float32 CUDA tensor")
+    N, Lq, M, L, P, _ = sampling_loc.shape
+    _require(M == n_heads, "n_heads mismatch")
+    rec = torch.empty((N, Lq, M, L, P, 3), dtype=torch.int64, device=sampling_loc.device)   # 24-byte records
+    with torch.cuda.device(sampling_loc.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _native.lib().msda_b200_sample_index_f32(sampling_loc.data_ptr(), spatial_shapes.data_ptr(),
+                                                      level_start_index.data_ptr(), N, Lq, M, d_head, L, P,
+                                                      rec.data_ptr(), stream)
+    _native.check(rc, "sample_index")
+    i32 = rec.view(torch.int32)                            # (..., 6)
+    return {"h_low": i32[..., 0], "w_low": i32[..., 1], "in_range": i32[..., 2], "corner_mask": i32[..., 3],
+            "level_offset": rec[..., 2]}
+
+
+def locations_softmax(spatial_shapes, reference_points, sampling_offsets, attention_logits, lanes_per_unit: int = 8):
+    """The fused kernel's glue arithmetic on its own: returns (sampling_locations, attention_weights)."""
+    N, Lq, M, L, P, _ = sampling_offsets.shape
+    ref_dim = reference_points.shape[-1]
+    if ref_dim not in (2, 4):
+        raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(ref_dim))
+    loc = torch.empty_like(sampling_offsets)
+    attn = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=sampling_offsets.device)
+    with torch.cuda.device(sampling_offsets.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _native.lib().msda_b200_locations_softmax_f32(
+            spatial_shapes.data_ptr(), reference_points.data_ptr(), ref_dim, sampling_offsets.data_ptr(),
+            attention_logits.data_ptr(), N, M, L, Lq, P, lanes_per_unit, loc.data_ptr(), attn.data_ptr(), stream)
+    _native.check(rc, "locations_softmax")
+    return loc, attn

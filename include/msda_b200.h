@@ -1,0 +1,161 @@
+/*
+ * msda_b200.h -- C-ABI of the B200-native (sm_100a) multi-scale deformable attention library.
+ *
+ * This is the drop-in boundary for the GoMatching / DeepSolo MSDeformAttn hot path.  It replaces,
+ * one for one, the native extension `adet._C` of the reference:
+ *
+ *   reference interface                                            replaced by
+ *   ------------------------------------------------------------   -----------------------------------
+ *   ms_deformable_im2col_cuda<scalar_t>(stream, value, shapes,      msda_b200_forward_f32
+ *     lsi, loc, attn, batch, spatial_size, heads, channels,         msda_b200_forward_bf16
+ *     levels, query, point, data_col)
+ *     third_party/adet/layers/csrc/DeformAttn/ms_deform_im2col_cuda.cuh:923-954
+ *   ms_deform_attn_cuda_forward(value, shapes, lsi, loc, attn,      (same two; the caller allocates the
+ *     im2col_step)   .../ms_deform_attn_cuda.cu:20-80                output, no memset, one launch for
+ *   adet._C.ms_deform_attn_forward   csrc/vision.cpp:52-53           all N -- im2col_step is accepted and
+ *   ms_deform_attn_forward dispatch  .../ms_deform_attn.h:20-39      ignored by the Python layer)
+ *   MSDeformAttn.forward glue (softmax over L*P, offsets ->         msda_b200_forward_fused_f32
+ *     locations, both reference_points forms)                       msda_b200_forward_fused_bf16
+ *     third_party/adet/layers/ms_deform_attn.py:137-152
+ *   ms_deformable_col2im_cuda / ms_deform_attn_cuda_backward        msda_b200_backward_f32
+ *     .../ms_deform_im2col_cuda.cuh:956-1327, ms_deform_attn_cuda.cu:83-153
+ *   adet._C.ms_deform_attn_backward  csrc/vision.cpp:54-55
+ *
+ * Conventions (identical to the reference launcher unless noted):
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; all tensors contiguous row-major
+ *   - value   (N, S, M, D)          S = sum_l H_l*W_l value tokens, M heads, D channels per head
+ *   - shapes  (L, 2) int64 [H, W]   read on the device, never copied to the host (no sync)
+ *   - lsi     (L,)   int64          level start index in tokens
+ *   - loc     (N, Lq, M, L, P, 2)   float32, x (width) first, y (height) second, normalised to [0,1]
+ *   - attn    (N, Lq, M, L, P)      float32
+ *   - out     (N, Lq, M*D)          written exactly once per element; need not be zero-initialised
+ *   - `stream` is a cudaStream_t passed as void*; the call only enqueues work (no synchronisation,
+ *     CUDA-graph capturable) and is re-entrant
+ *   - return value: 0 on success, a positive cudaError_t on a CUDA failure, a negative MSDA_E_* code on
+ *     an argument error.  msda_b200_error_string() describes either.
+ *   - the sampling-index contract (bit-exact with the reference binary built by nvcc 12.9 for sm_100a):
+ *       h_im = fmaf(loc_y, (float)H_l, -0.5f), w_im likewise; h_low = floor(h_im); a sample contributes
+ *       iff h_im > -1 && w_im > -1 && h_im < H && w_im < W; corners outside the map read as zero.
+ *   - there is NO CPU path: the library does arithmetic only on the GPU.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+/* argument errors (negative so they cannot collide with cudaError_t) */
+#define MSDA_E_NULLPTR   (-1)   /* a required pointer is NULL                                   */
+#define MSDA_E_DIMS      (-2)   /* a dimension is <= 0 or the product overflows 31-bit indexing */
+#define MSDA_E_ALIGN     (-3)   /* a pointer is not 16-byte aligned                             */
+#define MSDA_E_REFDIM    (-4)   /* reference_points last dim is neither 2 nor 4                 */
+#define MSDA_E_UNSUPPORTED (-5) /* combination has no kernel (e.g. bf16 with odd D)             */
+#define MSDA_E_NOCUDA    (-6)   /* no CUDA device / driver                                      */
+
+/* Optional launch tuning.  Pass NULL for the built-in heuristics.  Never changes results. */
+typedef struct msda_b200_tuning {
+  int32_t mode;          /* 0 auto | 1 linear query tiles | 2 pyramid 2-D tiles (needs Lq == S) | 3 generic kernel */
+  int32_t tile_h;        /* pyramid tile height in pixels (0 = default)                            */
+  int32_t tile_w;        /* pyramid tile width in pixels, multiple of 4 (0 = default)              */
+  int32_t tile_q;        /* linear tile length in queries (0 = default)                            */
+  int32_t ctas_per_sm;   /* persistent grid = SM count * ctas_per_sm (0 = default)                 */
+  int32_t variant;       /* kernel instantiation selector, see msda_b200_variant_count (0 = default)*/
+  int32_t reserved[2];
+} msda_b200_tuning_t;
+
+int         msda_b200_abi_version(void);
+const char* msda_b200_error_string(int code);
+/* number of SMs of the current device, or a negative error */
+int         msda_b200_sm_count(void);
+int         msda_b200_variant_count(void);
+
+/* ---- core operator: the _MSDeformAttnFunction boundary (ms_deform_attn.py:20-27) ------------------ */
+int msda_b200_forward_f32(const float* value, const int64_t* shapes, const int64_t* lsi,
+                          const float* loc, const float* attn,
+                          int N, int S, int M, int D, int L, int Lq, int P,
+                          float* out, void* stream);
+
+/* value/out stored as bf16 (raw uint16 bit patterns); loc/attn stay fp32; fp32 accumulation, one
+ * final round-to-nearest-even.  The reference has no half path (ms_deform_attn_cuda.cu:64): results
+ * equal the fp32 kernel applied to the up-cast value, rounded once. */
+int msda_b200_forward_bf16(const void* value_bf16, const int64_t* shapes, const int64_t* lsi,
+                           const float* loc, const float* attn,
+                           int N, int S, int M, int D, int L, int Lq, int P,
+                           void* out_bf16, void* stream);
+
+/* same two with explicit tuning (used by bench.py and the tests to pin a variant) */
+int msda_b200_forward_f32_ex(const float* value, const int64_t* shapes, const int64_t* lsi,
+                             const float* loc, const float* attn,
+                             int N, int S, int M, int D, int L, int Lq, int P,
+                             float* out, void* stream, const msda_b200_tuning_t* tuning);
+int msda_b200_forward_bf16_ex(const void* value_bf16, const int64_t* shapes, const int64_t* lsi,
+                              const float* loc, const float* attn,
+                              int N, int S, int M, int D, int L, int Lq, int P,
+                              void* out_bf16, void* stream, const msda_b200_tuning_t* tuning);
+
+/* ---- fused operator: softmax over L*P + offsets->locations + sampler in ONE kernel -----------------
+ *   ref      (N, Lq, L, ref_dim)  ref_dim 2: loc = ref + off / (W_l, H_l)
+ *                                 ref_dim 4: loc = ref[:2] + off / P * ref[2:] * 0.5
+ *   offsets  (N, Lq, M, L, P, 2)  raw output of the sampling_offsets projection
+ *   logits   (N, Lq, M, L*P)      raw output of the attention_weights projection (pre-softmax)
+ * Locations are formed with the same IEEE operations, in the same order, as the eager reference
+ * (true division, then add; no reciprocal, no FMA), so sampling indices stay bit-exact. */
+int msda_b200_forward_fused_f32(const float* value, const int64_t* shapes, const int64_t* lsi,
+                                const float* ref, int ref_dim, const float* offsets, const float* logits,
+                                int N, int S, int M, int D, int L, int Lq, int P,
+                                float* out, void* stream, const msda_b200_tuning_t* tuning);
+int msda_b200_forward_fused_bf16(const void* value_bf16, const int64_t* shapes, const int64_t* lsi,
+                                 const float* ref, int ref_dim, const float* offsets, const float* logits,
+                                 int N, int S, int M, int D, int L, int Lq, int P,
+                                 void* out_bf16, void* stream, const msda_b200_tuning_t* tuning);
+
+/* ---- glue kernels on their own (what the fused kernel does in registers), for tests/inspection ---- */
+/* loc_out (N,Lq,M,L,P,2), attn_out (N,Lq,M,L,P); either output may be NULL.  lanes_per_unit selects the
+ * lane layout being exercised: 8 = the fp32 D=32 kernels, 4 = the bf16 D=32 kernels, 16 = fp32 D=64. */
+int msda_b200_locations_softmax_f32(const int64_t* shapes, const float* ref, int ref_dim,
+                                    const float* offsets, const float* logits,
+                                    int N, int M, int L, int Lq, int P, int lanes_per_unit,
+                                    float* loc_out, float* attn_out, void* stream);
+
+/* ---- sampling-index dump: the SAME device function the forward kernels use ------------------------
+ * One record per sample (N,Lq,M,L,P), layout identical to oracle/msda_oracle.c msda_oracle_index_t:
+ *   int32 h_low, w_low, in_range, corner_mask ; int64 level_offset (= lsi[l]*M*D elements)
+ * (h_low/w_low/corner_mask are 0 when !in_range).  cuh:33-84, :272-296. */
+typedef struct msda_b200_index {
+  int32_t h_low, w_low, in_range, corner_mask;
+  int64_t level_offset;
+} msda_b200_index_t;
+int msda_b200_sample_index_f32(const float* loc, const int64_t* shapes, const int64_t* lsi,
+                               int N, int Lq, int M, int D, int L, int P,
+                               msda_b200_index_t* out, void* stream);
+
+/* ---- backward of the core operator (ms_deform_attn_cuda.cu:83-153; cuh:301-920) --------------------
+ * grad_value (N,S,M,D) MUST be zero-initialised by the caller (accumulated with atomics exactly like
+ * the reference); grad_loc (N,Lq,M,L,P,2) and grad_attn (N,Lq,M,L,P) are written once per element. */
+int msda_b200_backward_f32(const float* value, const int64_t* shapes, const int64_t* lsi,
+                           const float* loc, const float* attn, const float* grad_out,
+                           int N, int S, int M, int D, int L, int Lq, int P,
+                           float* grad_value, float* grad_loc, float* grad_attn, void* stream);
+
+/* ---- host-buffer entry: what a non-PyTorch host (the cgo/JNI/ctypes stub of INTEGRATION.md) calls --
+ * All tensor pointers are HOST pointers (pinned for full PCIe speed, pageable works).  Copies the
+ * inputs to a device workspace owned by the handle, runs the core forward, copies the result back,
+ * and synchronises the handle's stream before returning. */
+typedef struct msda_b200_host_ctx msda_b200_host_ctx_t;
+int  msda_b200_host_ctx_create(msda_b200_host_ctx_t** ctx, int device);
+void msda_b200_host_ctx_destroy(msda_b200_host_ctx_t* ctx);
+int  msda_b200_forward_f32_host(msda_b200_host_ctx_t* ctx,
+                                const float* value_host, const int64_t* shapes_host, const int64_t* lsi_host,
+                                const float* loc_host, const float* attn_host,
+                                int N, int S, int M, int D, int L, int Lq, int P,
+                                float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

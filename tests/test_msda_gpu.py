@@ -1,0 +1,352 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C-ABI library
+(gomatching_b200/libmsda_b200.so) via the Python operator layer; the checker is the CPU oracle
+(oracle/msda_oracle.c), the committed golden fixtures generated from the reference (tests/golden/), and --
+when oracle/_ref/libmsda_refcuda.so was built -- the unmodified reference CUDA kernel itself.
+
+Bars (BASELINE.json north_star): sampling indices and level offsets bit-exact; outputs within 1e-4
+(fp32) / 2e-2 (bf16) of the reference as max|a-b|/max|b|.  The fp32 and bf16 kernels reproduce the
+reference's FMA chain, so most output checks below are in fact bit-exact (np.array_equal).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, rel_err
+from oracle import msda_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CORE = Golden("core_cases.npz").names()
+MODULE = Golden("module_cases.npz").names()
+REFCUDA = os.path.join(ROOT, "oracle", "_ref", "libmsda_refcuda.so")
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def run_core(c, tuning=None, dtype=torch.float32):
+    import gomatching_b200 as g
+    out = g.ms_deform_attn_forward(dev(c["value"], dtype), dev(c["shapes"]), dev(c["lsi"]), dev(c["loc"]),
+                                   dev(c["attn"]), 64, tuning=tuning)
+    torch.cuda.synchronize()
+    return out
+
+
+def bits(t):
+    return t.view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def test_native_library_is_what_runs():
+    from gomatching_b200 import _native
+    L = _native.lib()
+    assert L.msda_b200_sm_count() >= 100          # B200: 148
+    assert os.path.basename(_native.LIB_PATH) == "libmsda_b200.so"
+
+
+@pytest.mark.parametrize("name", CORE)
+def test_core_fp32_bit_exact_vs_oracle_and_in_tolerance_vs_reference(core_cases, name):
+    c = core_cases.case(name)
+    out = run_core(c).cpu().numpy()
+    ora = O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"])
+    assert np.array_equal(out, ora), "fp32 kernel differs from the kernel-arithmetic oracle (max rel %g)" % rel_err(out, ora)
+    assert rel_err(out, c["out_f32"]) <= 1e-4      # vs the reference's own ms_deform_attn_core_pytorch output
+    assert rel_err(out, c["out_f64"]) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["uniform_d32", "edges_d32", "d64_p8"])
+def test_every_variant_and_mode_gives_identical_bits(core_cases, name):
+    from gomatching_b200 import _native
+    c = core_cases.case(name)
+    base = run_core(c).cpu().numpy()
+    for variant in range(_native.lib().msda_b200_variant_count()):
+        for mode in (1, 3):
+            for tq in (4, 32, 64):
+                out = run_core(c, dict(mode=mode, variant=variant, tile_q=tq, ctas_per_sm=2)).cpu().numpy()
+                assert np.array_equal(out, base), (variant, mode, tq)
+
+
+@pytest.mark.parametrize("name", ["uniform_d32", "edges_d32", "d64_p8", "nonpow2_d12"])
+def test_core_bf16_bit_exact_vs_oracle(core_cases, name):
+    c = core_cases.case(name)
+    vb = O.f32_to_bf16_bits(c["value"])
+    out = run_core(c, dtype=torch.bfloat16)
+    ora = O.forward_bf16(vb, c["shapes"], c["lsi"], c["loc"], c["attn"])
+    assert np.array_equal(bits(out), ora)
+    # north_star bf16 bar: 2e-2 relative vs the fp32 reference on the same inputs
+    assert rel_err(out.float().cpu().numpy(), c["out_f32"]) <= 2e-2
+
+
+@pytest.mark.parametrize("name", ["uniform_d32", "edges_d32", "wide_d32", "nonpow2_d12"])
+def test_sampling_indices_and_level_offsets_bit_exact(core_cases, name):
+    import gomatching_b200 as g
+    c = core_cases.case(name)
+    N, S, M, D = c["value"].shape
+    got = g.sample_index(dev(c["loc"]), dev(c["shapes"]), dev(c["lsi"]), M, D)
+    ora = O.sample_index(c["loc"], c["shapes"], c["lsi"], M=M, D=D)
+    for k in ("h_low", "w_low", "in_range", "corner_mask", "level_offset"):
+        assert np.array_equal(got[k].cpu().numpy(), ora[k]), k
+
+
+@pytest.mark.parametrize("tag", ["enc0", "dec0"])
+def test_setC_default_init_network_capture(setc_cases, tag):
+    """Samples sit exactly on pixel centres: the worst case for the fused-rounding index contract."""
+    import gomatching_b200 as g
+    c = setc_cases.case(tag)
+    out = run_core(c).cpu().numpy()
+    assert np.array_equal(out, O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"]))
+    assert rel_err(out, c["out"]) <= 1e-4
+    got = g.sample_index(dev(c["loc"]), dev(c["shapes"]), dev(c["lsi"]), 8, 32)
+    ora = O.sample_index(c["loc"], c["shapes"], c["lsi"], M=8, D=32)
+    for k in ("h_low", "w_low", "in_range", "corner_mask", "level_offset"):
+        assert np.array_equal(got[k].cpu().numpy(), ora[k]), k
+    if tag == "enc0":      # Lq == S: the pyramid tiling is the default; force the others too
+        for tuning in (dict(mode=1), dict(mode=2, tile_h=4, tile_w=4), dict(mode=2, tile_h=16, tile_w=16), dict(mode=3)):
+            assert np.array_equal(run_core(c, tuning).cpu().numpy(), out), tuning
+
+
+# ---------------------------------------------------------------------------------------------------
+# Full-size workloads (BASELINE.json configs 1-3): oracle on the host, reference CUDA kernel when built
+# ---------------------------------------------------------------------------------------------------
+def _refcuda():
+    if not os.path.exists(REFCUDA):
+        return None
+    lib = ctypes.CDLL(REFCUDA)
+    lib.refcuda_msda_forward_f32.restype = ctypes.c_int
+    lib.refcuda_msda_forward_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 7 + [ctypes.c_void_p] * 2
+    return lib
+
+
+def _run_refcuda(lib, w):
+    N, S, M, D, L, Lq, P = w.dims
+    v, sh, ls, loc, at = dev(w.value), dev(w.shapes), dev(w.lsi), dev(w.loc), dev(w.attn)
+    out = torch.empty(N, Lq, M * D, device="cuda")
+    rc = lib.refcuda_msda_forward_f32(v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), at.data_ptr(), N, S, M,
+                                      D, L, Lq, P, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("kind,dist,n", [("encoder", "local", 1), ("encoder", "uniform", 1), ("decoder", "local", 1),
+                                         ("decoder", "uniform", 2), ("encoder", "local", 2)])
+def test_full_size_720p_bit_exact(kind, dist, n):
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload(kind, 720, 1280, n=n, seed=11, dist=dist)
+    c = dict(value=w.value.numpy(), shapes=w.shapes.numpy(), lsi=w.lsi.numpy(), loc=w.loc.numpy(), attn=w.attn.numpy())
+    out = run_core(c)
+    ora = O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"])
+    assert np.array_equal(out.cpu().numpy(), ora)
+    # index parity at full size
+    got = g.sample_index(dev(w.loc), dev(w.shapes), dev(w.lsi), 8, 32)
+    oi = O.sample_index(c["loc"], c["shapes"], c["lsi"], M=8, D=32)
+    for k in ("h_low", "w_low", "in_range", "corner_mask", "level_offset"):
+        assert np.array_equal(got[k].cpu().numpy(), oi[k]), k
+    # the reference's CPU path (grid_sample port) agrees within the fp32 bar
+    gs = O.core_gridsample(w.value, w.shapes.tolist(), w.loc, w.attn).numpy()
+    assert rel_err(out.cpu().numpy(), gs) <= 1e-4
+    ref = _refcuda()
+    if ref is not None:    # the unmodified reference kernel, compiled for sm_100a from /root/reference
+        assert torch.equal(out, _run_refcuda(ref, w)), "differs from the reference CUDA kernel"
+    # bf16 storage: bit-exact vs the oracle, inside 2e-2 of fp32
+    ob = run_core(c, dtype=torch.bfloat16)
+    assert np.array_equal(bits(ob), O.forward_bf16(O.f32_to_bf16_bits(c["value"]), c["shapes"], c["lsi"], c["loc"], c["attn"]))
+    assert rel_err(ob.float().cpu().numpy(), ora) <= 2e-2
+
+
+def test_reference_cuda_kernel_available_for_parity():
+    """Not a failure if absent (it is built only where /root/reference exists) -- but say so loudly."""
+    if _refcuda() is None:
+        pytest.skip("oracle/_ref/libmsda_refcuda.so not built: parity vs the reference CUDA binary not exercised")
+
+
+def test_1080p_encoder_properties():
+    """Config 5 size: batch-split invariance, query-permutation equivariance, linearity in value."""
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("encoder", 1080, 1920, n=2, seed=5, dist="local")
+    v, sh, ls, loc, at = dev(w.value), dev(w.shapes), dev(w.lsi), dev(w.loc), dev(w.attn)
+    out = g.ms_deform_attn_forward(v, sh, ls, loc, at, 64)
+    # (1) a batch of 2 equals two batches of 1, bit for bit
+    for b in range(2):
+        ob = g.ms_deform_attn_forward(v[b:b + 1].contiguous(), sh, ls, loc[b:b + 1].contiguous(), at[b:b + 1].contiguous(), 64)
+        assert torch.equal(ob[0], out[b])
+    # (2) permuting the queries permutes the output rows (tiling never mixes queries)
+    perm = torch.randperm(loc.shape[1], generator=torch.Generator().manual_seed(3)).cuda()
+    op = g.ms_deform_attn_forward(v, sh, ls, loc[:, perm].contiguous(), at[:, perm].contiguous(), 64)
+    assert torch.equal(op, out[:, perm])
+    # (3) linear in value: f(2v) == 2 f(v) exactly (power-of-two scaling commutes with every rounding)
+    assert torch.equal(g.ms_deform_attn_forward(v * 2, sh, ls, loc, at, 64), out * 2)
+    # (4) value == 1 everywhere: out = sum over in-range samples of attn * (sum of valid corner weights) <= 1
+    ones = torch.ones_like(v)
+    o1 = g.ms_deform_attn_forward(ones, sh, ls, loc, at, 64)
+    assert float(o1.max()) <= 1.0 + 1e-5 and float(o1.min()) >= 0.0
+    assert torch.equal(o1.view(2, -1, 8, 32)[..., :1].expand(-1, -1, -1, 32), o1.view(2, -1, 8, 32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fused glue: softmax + offsets->locations inside the sampler
+# ---------------------------------------------------------------------------------------------------
+def _eager_glue(w_ref, off, logits, shapes, P):
+    """ms_deform_attn.py:138-147 with torch on the GPU (what the reference executes)."""
+    N, Lq, M, L, _, _ = off.shape
+    attn = torch.softmax(logits, -1).view(N, Lq, M, L, P)
+    if w_ref.shape[-1] == 2:
+        norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        loc = w_ref[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = w_ref[:, :, None, :, None, :2] + off / P * w_ref[:, :, None, :, None, 2:] * 0.5
+    return loc.contiguous(), attn.contiguous()
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("lanes", [8, 4])
+def test_glue_kernel_locations_bit_exact_softmax_matches_torch(ref_dim, lanes):
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("decoder", 720, 1280, n=2, seed=21, dist="local")
+    ref = w.ref
+    if ref_dim == 4:
+        gen = torch.Generator().manual_seed(2)
+        ref = torch.cat([w.ref, torch.rand(w.ref.shape, generator=gen) * 0.3 + 0.05], -1).contiguous()
+    sh, off, lg, rf = dev(w.shapes), dev(w.offsets), dev(w.logits), dev(ref)
+    loc, attn = g.locations_softmax(sh, rf, off, lg, lanes_per_unit=lanes)
+    eloc, eattn = _eager_glue(rf, off, lg, sh, 4)
+    assert torch.equal(loc, eloc), "locations differ from the eager reference arithmetic"
+    # and therefore the CPU oracle's restatement too
+    assert np.array_equal(loc.cpu().numpy(), O.locations(ref.numpy(), w.offsets.numpy(), w.shapes.numpy()))
+    # softmax: same operation order as torch's warp softmax -> expect identical bits; bar is 1e-6 relative
+    assert rel_err(attn.cpu().numpy(), eattn.cpu().numpy()) <= 1e-6
+    frac_equal = float((attn == eattn).float().mean())
+    print("softmax bit-identical fraction vs torch: %.6f" % frac_equal)
+    assert frac_equal > 0.99
+
+
+@pytest.mark.parametrize("kind,dtype", [("encoder", torch.float32), ("decoder", torch.float32),
+                                        ("encoder", torch.bfloat16), ("decoder", torch.bfloat16)])
+def test_fused_equals_unfused(kind, dtype):
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload(kind, 360, 640, n=2, seed=4, dist="local")
+    v, sh, ls = dev(w.value, dtype), dev(w.shapes), dev(w.lsi)
+    rf, off, lg = dev(w.ref), dev(w.offsets), dev(w.logits)
+    fused = g.ms_deform_attn_forward_fused(v, sh, ls, rf, off, lg)
+    lanes = 8 if dtype == torch.float32 else 4
+    loc, attn = g.locations_softmax(sh, rf, off, lg, lanes_per_unit=lanes)
+    unfused = g.ms_deform_attn_forward(v, sh, ls, loc, attn, 64)
+    assert torch.equal(fused, unfused)          # same arithmetic, same order -> same bits
+    eloc, eattn = _eager_glue(rf, off, lg, sh, 4)
+    eager = g.ms_deform_attn_forward(v, sh, ls, eloc, eattn, 64)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert rel_err(fused.float().cpu().numpy(), eager.float().cpu().numpy()) <= tol
+    # against the CPU oracle end to end (fp32 only, it is the reference arithmetic)
+    if dtype == torch.float32:
+        ora = O.forward_f32(w.value.numpy(), w.shapes.numpy(), w.lsi.numpy(),
+                            O.locations(w.ref.numpy(), w.offsets.numpy(), w.shapes.numpy()),
+                            O.softmax(w.logits.numpy()).reshape(w.attn.shape))
+        assert rel_err(fused.cpu().numpy(), ora) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# Module drop-in
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", MODULE)
+@pytest.mark.parametrize("fused", [True, False])
+def test_module_matches_reference_module_output(module_cases, name, fused):
+    import gomatching_b200 as g
+    c = module_cases.case(name)
+    d_model, levels, heads, points = (int(v) for v in c["cfg"])
+    mod = g.MSDeformAttn(d_model, levels, heads, points)
+    mod.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("sd/")}, strict=True)
+    mod = mod.cuda().eval()
+    mod.use_fused = fused
+    mask = dev(c["mask"]) if c["mask"].size else None
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        out = mod(dev(c["query"]), dev(c["ref"]), dev(c["src"]), dev(c["shapes"]), dev(c["lsi"]), mask)
+    assert rel_err(out.cpu().numpy(), c["out"]) <= 1e-4      # reference MSDeformAttn.forward output (fp32 bar)
+
+
+def test_module_error_behaviour_matches_reference():
+    import gomatching_b200 as g
+    m = g.MSDeformAttn(256, 4, 8, 4).cuda()
+    sh = torch.tensor([[4, 4], [2, 2], [1, 1], [1, 1]]).cuda()
+    ls = torch.tensor([0, 16, 20, 21]).cuda()
+    with pytest.raises(ValueError, match="must be 2 or 4"):
+        m(torch.zeros(1, 3, 256).cuda(), torch.zeros(1, 3, 4, 3).cuda(), torch.zeros(1, 22, 256).cuda(), sh, ls)
+    # non-contiguous operator input (ms_deform_attn_cuda.cu:28)
+    v = torch.zeros(1, 22, 32, 8).cuda().transpose(2, 3)
+    with pytest.raises(RuntimeError, match="value tensor has to be contiguous"):
+        g.ms_deform_attn_forward(v, sh, ls, torch.zeros(1, 3, 8, 4, 4, 2).cuda(), torch.zeros(1, 3, 8, 4, 4).cuda(), 64)
+    # batch rule (ms_deform_attn_cuda.cu:50-52): N=65 is rejected exactly like the reference
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        g.ms_deform_attn_forward(torch.zeros(65, 22, 8, 32).cuda(), sh, ls, torch.zeros(65, 3, 8, 4, 4, 2).cuda(),
+                                 torch.zeros(65, 3, 8, 4, 4).cuda(), 64)
+    m.strict_shape_check = True
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 3, 256).cuda(), torch.zeros(1, 3, 4, 2).cuda(), torch.zeros(1, 23, 256).cuda(), sh, ls)
+
+
+def test_batch_64_and_empty_like_edges(core_cases):
+    """N=64 (= im2col_step) in one launch; a level of 1x1; queries whose samples are all out of range."""
+    import gomatching_b200 as g
+    gen = torch.Generator().manual_seed(9)
+    shapes = [(3, 5), (1, 1)]
+    S = 16
+    v = torch.randn(64, S, 2, 32, generator=gen)
+    loc = torch.rand(64, 7, 2, 2, 4, 2, generator=gen) * 1.4 - 0.2
+    loc[:, 0] = 5.0                       # every sample of query 0 is out of range -> exact zeros
+    loc[:, 1] = float("nan")              # NaN locations fail every comparison -> skipped (cuh:288)
+    attn = torch.softmax(torch.randn(64, 7, 2, 8, generator=gen), -1).view(64, 7, 2, 2, 4)
+    sh = torch.tensor(shapes)
+    ls = torch.tensor([0, 15])
+    out = g.ms_deform_attn_forward(v.cuda(), sh.cuda(), ls.cuda(), loc.cuda(), attn.cuda(), 64).cpu().numpy()
+    ora = O.forward_f32(v.numpy(), sh.numpy(), ls.numpy(), loc.numpy(), attn.numpy())
+    assert np.array_equal(out, ora)
+    assert not out[:, :2].any()
+
+
+def test_cuda_graph_capture_and_side_stream(core_cases):
+    """The call only enqueues work on the current stream: capturable, no hidden sync or allocation."""
+    import gomatching_b200 as g
+    c = core_cases.case("uniform_d32")
+    v, sh, ls, loc, at = dev(c["value"]), dev(c["shapes"]), dev(c["lsi"]), dev(c["loc"]), dev(c["attn"])
+    eager = g.ms_deform_attn_forward(v, sh, ls, loc, at, 64)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        warm = g.ms_deform_attn_forward(v, sh, ls, loc, at, 64)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        captured = g.ms_deform_attn_forward(v, sh, ls, loc, at, 64)
+    captured.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager) and torch.equal(warm, eager)
+
+
+def test_host_buffer_entry_point(core_cases):
+    """msda_b200_forward_f32_host: the call a non-PyTorch host makes."""
+    from gomatching_b200 import _native
+    L = _native.lib()
+    c = core_cases.case("uniform_d32")
+    N, S, M, D = c["value"].shape
+    _, Lq, _, Lv, P, _ = c["loc"].shape
+    ctx = ctypes.c_void_p()
+    assert L.msda_b200_host_ctx_create(ctypes.byref(ctx), 0) == 0
+    out = np.empty((N, Lq, M * D), np.float32)
+    arrs = [np.ascontiguousarray(c[k]) for k in ("value", "shapes", "lsi", "loc", "attn")]
+    rc = L.msda_b200_forward_f32_host(ctx, *[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], N, S, M, D, Lv, Lq, P,
+                                      out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    L.msda_b200_host_ctx_destroy(ctx)
+    assert np.array_equal(out, O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"]))
