@@ -115,5 +115,8 @@ def make_tuning(tuning) -> "ctypes.POINTER(Tuning) | None":
         return ctypes.pointer(tuning)
     t = Tuning()
     for k, v in dict(tuning).items():
-        setattr(t, k, int(v))
+        if k == "force_v1":            # reserved[0] = 1: run the runtime-L*P tiled kernel instead of the specialised one
+            t.reserved[0] = int(v)
+        else:
+            setattr(t, k, int(v))
     return ctypes.pointer(t)

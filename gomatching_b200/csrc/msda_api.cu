@@ -55,6 +55,7 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
   if (mode == kModeGeneric && fused) return MSDA_E_UNSUPPORTED;
   p.mode = mode;
   p.variant = tn ? tn->variant : 0;
+  p.force_v1 = (tn && tn->reserved[0] == 1) ? 1 : 0;
   if (p.variant < 0 || p.variant >= forward_variant_count()) p.variant = 0;
   int th = (tn && tn->tile_h > 0) ? tn->tile_h : 8;
   int tw = (tn && tn->tile_w > 0) ? tn->tile_w : 16;

@@ -28,9 +28,9 @@ struct SampleGeom {
   bool in_range;       // cuh:288
 };
 
-__device__ __forceinline__ SampleGeom sample_setup(float loc_w, float loc_h, int H, int W) {
+// Level sizes are passed both as int and as the (exact) float the reference converts them to.
+__device__ __forceinline__ SampleGeom sample_setup_f(float loc_w, float loc_h, float Hf, float Wf, int H, int W) {
   SampleGeom g;
-  const float Hf = (float)H, Wf = (float)W;
   const float h_im = __fmaf_rn(loc_h, Hf, -0.5f);
   const float w_im = __fmaf_rn(loc_w, Wf, -0.5f);
   g.in_range = (h_im > -1.0f) && (w_im > -1.0f) && (h_im < Hf) && (w_im < Wf);
@@ -46,6 +46,10 @@ __device__ __forceinline__ SampleGeom sample_setup(float loc_w, float loc_h, int
     g.mask = (int)(t && l) | ((int)(t && r) << 1) | ((int)(b && l) << 2) | ((int)(b && r) << 3);
   }
   return g;
+}
+
+__device__ __forceinline__ SampleGeom sample_setup(float loc_w, float loc_h, int H, int W) {
+  return sample_setup_f(loc_w, loc_h, (float)H, (float)W, H, W);
 }
 
 // The four bilinear weights in the reference's order (cuh:80): w1=hh*hw w2=hh*lw w3=lh*hw w4=lh*lw
@@ -94,6 +98,20 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
   float r;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
+}
+// 256-bit global load (sm_100a LDG.E.256): 4 lanes cover one 128-byte fp32 row, a warp gathers 8 rows per instruction
+struct __align__(32) Vec32B { uint4 lo, hi; };
+__device__ __forceinline__ void ld_value32(const void* p, Vec32B& r) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "+r"(r.lo.x), "+r"(r.lo.y), "+r"(r.lo.z), "+r"(r.lo.w), "+r"(r.hi.x), "+r"(r.hi.y), "+r"(r.hi.z), "+r"(r.hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_value16_keep(const void* p, uint4& r) {
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p));
+}
+__device__ __forceinline__ void st_stream32(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
 }
 __device__ __forceinline__ void st_stream16(void* p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

@@ -386,6 +386,8 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
     return (int)cudaGetLastError();
   }
   const int LP = p.L * p.P;
+  if (fast_supported(p.D, p.L, p.P) && !p.force_v1)
+    return sizeof(T) == 4 ? launch_forward_fast_f32(p, stream) : launch_forward_fast_bf16(p, stream);
   if (p.D == 32) {
     if (!fused) return dispatch_variant<T, 32, 0>(p, stream);
     if (LP == 16) return dispatch_variant<T, 32, 16>(p, stream);

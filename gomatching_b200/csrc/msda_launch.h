@@ -27,12 +27,17 @@ struct FwdParams {
   int tile_h, tile_w_log2;    // pyramid tile
   int grid;                   // CTAs to launch
   int variant;                // kernel instantiation
+  int force_v1;               // use the runtime-L*P tiled kernel even where the specialised one applies
 };
 
 // Each returns a cudaError_t cast to int (0 = ok) or MSDA_E_UNSUPPORTED (-5).
 int launch_forward_f32(const FwdParams& p, cudaStream_t stream);
 int launch_forward_bf16(const FwdParams& p, cudaStream_t stream);
 int forward_variant_count();
+// compile-time-specialised kernels for the DeepSolo configuration (msda_forward_fast.cu)
+bool fast_supported(int D, int L, int P);
+int launch_forward_fast_f32(const FwdParams& p, cudaStream_t stream);
+int launch_forward_fast_bf16(const FwdParams& p, cudaStream_t stream);
 // true if the tiled kernels can run this problem (else only the generic kernel can)
 bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused);
 

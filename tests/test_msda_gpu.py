@@ -69,8 +69,9 @@ def test_every_variant_and_mode_gives_identical_bits(core_cases, name):
     for variant in range(_native.lib().msda_b200_variant_count()):
         for mode in (1, 3):
             for tq in (4, 32, 64):
-                out = run_core(c, dict(mode=mode, variant=variant, tile_q=tq, ctas_per_sm=2)).cpu().numpy()
-                assert np.array_equal(out, base), (variant, mode, tq)
+                for v1 in (0, 1):
+                    out = run_core(c, dict(mode=mode, variant=variant, tile_q=tq, ctas_per_sm=2, force_v1=v1)).cpu().numpy()
+                    assert np.array_equal(out, base), (variant, mode, tq, v1)
 
 
 @pytest.mark.parametrize("name", ["uniform_d32", "edges_d32", "d64_p8", "nonpow2_d12"])
@@ -108,7 +109,8 @@ def test_setC_default_init_network_capture(setc_cases, tag):
     for k in ("h_low", "w_low", "in_range", "corner_mask", "level_offset"):
         assert np.array_equal(got[k].cpu().numpy(), ora[k]), k
     if tag == "enc0":      # Lq == S: the pyramid tiling is the default; force the others too
-        for tuning in (dict(mode=1), dict(mode=2, tile_h=4, tile_w=4), dict(mode=2, tile_h=16, tile_w=16), dict(mode=3)):
+        for tuning in (dict(mode=1), dict(mode=2, tile_h=4, tile_w=4), dict(mode=2, tile_h=16, tile_w=16), dict(mode=3),
+                       dict(mode=2, force_v1=1), dict(mode=2, variant=3), dict(mode=2, variant=5, tile_h=2, tile_w=32)):
             assert np.array_equal(run_core(c, tuning).cpu().numpy(), out), tuning
 
 

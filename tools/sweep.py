@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--iters", type=int, default=24)
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--force-v1", type=int, default=0)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -74,7 +75,7 @@ def main():
                   [(4, 8), (4, 16), (8, 8), (8, 16), (16, 8), (16, 16), (8, 32), (16, 32), (4, 32), (2, 32), (32, 32)]]
     tiles += [dict(mode=1, tile_q=q) for q in (16, 32, 64, 128, 256)]
     for v, t, cps in itertools.product(variants, tiles, cps_list):
-        tn = dict(t, variant=v, ctas_per_sm=cps)
+        tn = dict(t, variant=v, ctas_per_sm=cps, force_v1=args.force_v1)
         try:
             us = time_launches(runner(tn), sets, args.iters)
         except Exception as e:  # noqa: BLE001
