@@ -204,10 +204,14 @@ def device_workload(kind, frames, seed, dist, device):
     value = torch.randn(frames, S, M, D, generator=g, device=device)
     logits = torch.randn(frames, Lq, M, L * P, generator=g, device=device)
     if dist == "local":
-        offsets = torch.randn(frames, Lq, M, L, P, 2, generator=g, device=device) * 2.0
+        offsets = torch.randn(frames, Lq, M, L, P, 2, generator=g, device=device) * float(os.environ.get("MSDA_SIGMA_PX", "2.0"))
         offsets += syn.compass_offsets(M, L, P).to(device)[None, None]
     else:
         target = torch.rand(frames, Lq, M, L, P, 2, generator=g, device=device) * 1.2 - 0.1
+        if dist == "oor":          # diagnostic: every sample out of range -> no gather at all
+            target = target + 5.0
+        elif dist == "center":     # diagnostic: every sample at the map centre -> one hot cache line per level
+            target = target * 0.0 + 0.5
         offsets = (target - ref[:, :, None, :, None, :]) * wh[None, None, None, :, None, :]
     return {"kind": kind, "value": value, "ref": ref, "offsets": offsets.contiguous(), "logits": logits,
             "shapes": shapes.to(device), "lsi": syn.level_start_index(shapes_l).to(device), "Lq": Lq, "S": S}

@@ -54,12 +54,14 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
   }
   if (mode == kModeGeneric && fused) return MSDA_E_UNSUPPORTED;
   p.mode = mode;
-  p.variant = tn ? tn->variant : 0;
+  // defaults from the B200 sweeps (profiles/r01_sweep_*): encoder = pyramid 16x16 tiles with 16-warp CTAs,
+  // everything else = 64-query linear tiles with 8-warp CTAs
+  p.variant = tn ? tn->variant : (mode == kModePyramid ? 0 : 1);
   p.force_v1 = (tn && tn->reserved[0] == 1) ? 1 : 0;
   if (p.variant < 0 || p.variant >= forward_variant_count()) p.variant = 0;
-  int th = (tn && tn->tile_h > 0) ? tn->tile_h : 8;
+  int th = (tn && tn->tile_h > 0) ? tn->tile_h : 16;
   int tw = (tn && tn->tile_w > 0) ? tn->tile_w : 16;
-  int tq = (tn && tn->tile_q > 0) ? tn->tile_q : 32;
+  int tq = (tn && tn->tile_q > 0) ? tn->tile_q : 64;
   int cps = (tn && tn->ctas_per_sm > 0) ? tn->ctas_per_sm : 4;
   p.tile_w_log2 = ilog2_floor(tw < 4 ? 4 : tw);
   p.tile_h = th;

@@ -372,6 +372,10 @@ int dispatch_variant(const FwdParams& p, cudaStream_t stream) {
     case 3: return launch_tiled<T, D, 16, 4, LPT, 1>(p, stream);
     case 4: return launch_tiled<T, D, 8, 1, LPT, 4>(p, stream);
     case 5: return launch_tiled<T, D, 4, 2, LPT, 6>(p, stream);
+    case 6: return launch_tiled<T, D, 8, 1, LPT, 3>(p, stream);
+    case 7: return launch_tiled<T, D, 4, 1, LPT, 8>(p, stream);
+    case 8: return launch_tiled<T, D, 16, 1, LPT, 2>(p, stream);
+    case 9: return launch_tiled<T, D, 16, 2, LPT, 1>(p, stream);
   }
 }
 
@@ -405,7 +409,7 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int forward_variant_count() { return 6; }
+int forward_variant_count() { return 10; }
 
 bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused) {
   if (D != 32 && D != 64) return false;
