@@ -1,0 +1,9 @@
+"""Frame-sharded video inference around the MSDeformAttn hot path."""
+from .gather import gather_records
+from .pipeline import reference_association_step, run_clip, spot_chunk
+from .records import GOMATCHING_FIELDS, Field, RecordSchema
+from .sharding import CHUNK_FRAMES, chunk_ranges, frame_owner, frames_of_rank, slot_of_frame, slots_per_rank
+
+__all__ = ["gather_records", "reference_association_step", "run_clip", "spot_chunk", "GOMATCHING_FIELDS", "Field",
+           "RecordSchema", "CHUNK_FRAMES", "chunk_ranges", "frame_owner", "frames_of_rank", "slot_of_frame",
+           "slots_per_rank"]

@@ -352,3 +352,97 @@ def test_host_buffer_entry_point(core_cases):
     assert rc == 0
     L.msda_b200_host_ctx_destroy(ctx)
     assert np.array_equal(out, O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Backward (the "next" row a13): vs the reference CPU path under autograd
+# ---------------------------------------------------------------------------------------------------
+BACKWARD = Golden("backward_cases.npz").names()
+
+
+@pytest.mark.parametrize("name", BACKWARD)
+def test_backward_matches_reference_autograd(name):
+    import gomatching_b200 as g
+    c = Golden("backward_cases.npz").case(name)
+    value = dev(c["value"]).requires_grad_(True)
+    loc = dev(c["loc"]).requires_grad_(True)
+    attn = dev(c["attn"]).requires_grad_(True)
+    out = g.MSDeformAttnFunction.apply(value, dev(c["shapes"]), dev(c["lsi"]), loc, attn, 64)
+    out.backward(dev(c["grad_out"]))
+    torch.cuda.synchronize()
+    # fp32 kernels vs float64 reference gradients: the north_star fp32 bar (1e-4, max|a-b|/max|b|)
+    assert rel_err(out.detach().cpu().numpy(), c["out"]) <= 1e-4
+    assert rel_err(value.grad.cpu().numpy(), c["grad_value"]) <= 1e-4
+    assert rel_err(attn.grad.cpu().numpy(), c["grad_attn"]) <= 1e-4
+    # grad_loc multiplies by the level size (up to 160 px): same relative bar against its own scale
+    assert rel_err(loc.grad.cpu().numpy(), c["grad_loc"]) <= 1e-4
+
+
+def test_backward_full_size_decoder_vs_autograd_of_cpu_path():
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("decoder", 360, 640, n=1, seed=8, dist="local")
+    gen = torch.Generator().manual_seed(1)
+    go = torch.randn(1, w.loc.shape[1], 256, generator=gen)
+    v = w.value.clone().requires_grad_(True)
+    lo = w.loc.clone().requires_grad_(True)
+    at = w.attn.clone().requires_grad_(True)
+    O.core_gridsample(v, w.shapes.tolist(), lo, at).backward(go)
+    vg, lg, ag = dev(w.value).requires_grad_(True), dev(w.loc).requires_grad_(True), dev(w.attn).requires_grad_(True)
+    g.MSDeformAttnFunction.apply(vg, dev(w.shapes), dev(w.lsi), lg, ag, 64).backward(go.cuda())
+    assert rel_err(vg.grad.cpu().numpy(), v.grad.numpy()) <= 1e-4
+    assert rel_err(ag.grad.cpu().numpy(), at.grad.numpy()) <= 1e-4
+    assert rel_err(lg.grad.cpu().numpy(), lo.grad.numpy()) <= 1e-3      # fp32 vs fp32, location gradients x160
+
+
+def test_module_trains_through_the_autograd_function():
+    """With grad enabled the module takes the reference's eager glue + MSDeformAttnFunction path."""
+    import gomatching_b200 as g
+    m = g.MSDeformAttn(256, 4, 8, 4).cuda()
+    sh = torch.tensor([[8, 12], [4, 6], [2, 3], [1, 2]]).cuda()
+    ls = torch.tensor([0, 96, 120, 126]).cuda()
+    q = torch.randn(2, 5, 256, device="cuda", requires_grad=True)
+    src = torch.randn(2, 128, 256, device="cuda", requires_grad=True)
+    ref = torch.rand(2, 5, 4, 2, device="cuda")
+    out = m(q, ref, src, sh, ls)
+    out.square().mean().backward()
+    assert q.grad is not None and src.grad is not None and m.value_proj.weight.grad is not None
+    assert torch.isfinite(q.grad).all() and float(src.grad.abs().sum()) > 0
+    with torch.no_grad():
+        fused = m(q, ref, src, sh, ls)
+    assert rel_err(fused.cpu().numpy(), out.detach().cpu().numpy()) <= 1e-5
+
+
+def test_nccl_gather_of_frame_records_two_gpus(tmp_path):
+    """The exchange step on real NVLink (needs >= 2 GPUs; the driver's scaling run has them)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("single-GPU box")
+    import subprocess
+    import sys
+    code = (
+        "import os,torch,torch.distributed as dist\n"
+        "from gomatching_b200 import video as V\n"
+        "r=int(os.environ['RANK']);torch.cuda.set_device(r);dist.init_process_group('nccl')\n"
+        "s=V.RecordSchema(max_instances=8)\n"
+        "def spot(f,t):\n"
+        "    g=torch.Generator().manual_seed(t);n=t%5\n"
+        "    return ({'reid_features':torch.randn(n,1024,generator=g).cuda(),'pred_boxes':torch.rand(n,4,generator=g).cuda(),"
+        "'scores':torch.rand(n,generator=g).cuda(),'pred_classes':torch.zeros(n,dtype=torch.int64).cuda(),"
+        "'ctrl_points':torch.rand(n,50,generator=g).cuda(),'recs':torch.randint(0,9,(n,25),generator=g).cuda(),"
+        "'bd':torch.rand(n,25,4,generator=g).cuda()},(720,1280))\n"
+        "def asso(d,st,state):\n"
+        "    state=state or []\n"
+        "    state+= [(x['frame_index'],float(x['fields']['reid_features'].sum())) for x in d];return state\n"
+        "st=V.run_clip(list(range(11)),spot,asso,s,chunk=4,device='cuda')\n"
+        "if r==0:\n"
+        "    assert [a for a,_ in st]==list(range(11))\n"
+        "    import torch as T\n"
+        "    for t,v in st: assert abs(v-float(spot(None,t)[0]['reid_features'].sum()))<1e-3\n"
+        "    print('ok')\n"
+        "dist.destroy_process_group()\n")
+    script = tmp_path / "nccl_gather.py"
+    script.write_text("import sys\nsys.path.insert(0, %r)\n" % ROOT + code)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True,
+                       text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
