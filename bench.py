@@ -382,7 +382,7 @@ def main():
     enc_mean_ms = sum(enc_ms) / len(enc_ms)
     achieved = b_alg / (enc_mean_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "msda_fwd_tiled_kernel<float,32,...> encoder launch (N=%d, Lq=S=%d)" % (F, enc[0]["S"]),
+                "traffic": None, "kernel": "msda_fwd_fast_kernel<float,32,...,FUSED> encoder launch (N=%d, Lq=S=%d)" % (F, enc[0]["S"]),
                 "algorithmic_bytes_per_launch": b_alg, "mean_launch_us": enc_mean_ms * 1e3,
                 "launches_timed": len(enc_ms), "peak_source": peak_src,
                 "gather_bytes_per_launch": 4 * F * enc[0]["Lq"] * M * L * P * D * 4}
@@ -407,7 +407,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, generated on device)",
         "config": workload_config(args, F), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": args.steps * (ENC_LAYERS + DEC_LAYERS), "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": world * args.steps * (ENC_LAYERS + DEC_LAYERS), "roofline": roofline, "cpu_baseline": cpu,
         "msda_hbm_gbs": achieved,
     }
     print(json.dumps(line), flush=True)

@@ -19,10 +19,13 @@ SYMBOLS = (
     "msda_b200_variant_count",
     "msda_b200_forward_f32",
     "msda_b200_forward_bf16",
+    "msda_b200_forward_f64",
     "msda_b200_forward_f32_ex",
     "msda_b200_forward_bf16_ex",
     "msda_b200_forward_fused_f32",
     "msda_b200_forward_fused_bf16",
+    "msda_b200_forward_fused_pitched_f32",
+    "msda_b200_forward_fused_pitched_bf16",
     "msda_b200_locations_softmax_f32",
     "msda_b200_sample_index_f32",
     "msda_b200_backward_f32",
@@ -73,7 +76,7 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_sm_count.restype = ci
         L.msda_b200_variant_count.restype = ci
         core = [vp, vp, vp, vp, vp] + [ci] * 7 + [vp, vp]
-        for name in ("msda_b200_forward_f32", "msda_b200_forward_bf16"):
+        for name in ("msda_b200_forward_f32", "msda_b200_forward_bf16", "msda_b200_forward_f64"):
             getattr(L, name).restype = ci
             getattr(L, name).argtypes = core
         for name in ("msda_b200_forward_f32_ex", "msda_b200_forward_bf16_ex"):
@@ -83,6 +86,10 @@ def lib() -> ctypes.CDLL:
         for name in ("msda_b200_forward_fused_f32", "msda_b200_forward_fused_bf16"):
             getattr(L, name).restype = ci
             getattr(L, name).argtypes = fused
+        pitched = [vp, vp, vp, vp, ci, vp, ci, vp, ci] + [ci] * 7 + [vp, vp, ctypes.POINTER(Tuning)]
+        for name in ("msda_b200_forward_fused_pitched_f32", "msda_b200_forward_fused_pitched_bf16"):
+            getattr(L, name).restype = ci
+            getattr(L, name).argtypes = pitched
         L.msda_b200_locations_softmax_f32.restype = ci
         L.msda_b200_locations_softmax_f32.argtypes = [vp, vp, ci, vp, vp] + [ci] * 6 + [vp, vp, vp]
         L.msda_b200_sample_index_f32.restype = ci

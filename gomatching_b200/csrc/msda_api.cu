@@ -77,7 +77,8 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
 
 int forward_common(const void* value, const int64_t* shapes, const int64_t* lsi, const float* loc, const float* attn,
                    const float* ref, int ref_dim, const float* offsets, const float* logits, int N, int S, int M, int D,
-                   int L, int Lq, int P, void* out, void* stream, const msda_b200_tuning_t* tn, int elem_bytes) {
+                   int L, int Lq, int P, void* out, void* stream, const msda_b200_tuning_t* tn, int elem_bytes,
+                   int off_pitch = 0, int logit_pitch = 0) {
   const bool fused = (loc == nullptr);
   if (!value || !shapes || !lsi || !out) return MSDA_E_NULLPTR;
   if (fused) {
@@ -93,8 +94,14 @@ int forward_common(const void* value, const int64_t* shapes, const int64_t* lsi,
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.attn = attn;
   p.ref = ref; p.offsets = offsets; p.logits = logits; p.ref_dim = ref_dim; p.out = out;
   p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P;
+  p.off_pitch = off_pitch > 0 ? off_pitch : M * L * P * 2;
+  p.logit_pitch = logit_pitch > 0 ? logit_pitch : M * L * P;
+  if (p.off_pitch < M * L * P * 2 || p.logit_pitch < M * L * P || (p.off_pitch & 1)) return MSDA_E_DIMS;
+  const bool pitched = fused && (p.off_pitch != M * L * P * 2 || p.logit_pitch != M * L * P);
+  if (pitched && !fast_supported(D, L, P)) return MSDA_E_UNSUPPORTED;   // only the specialised kernels take pitches
   rc = plan(p, elem_bytes, fused, tn);
   if (rc) return rc;
+  if (pitched && (p.mode == kModeGeneric || p.force_v1)) return MSDA_E_UNSUPPORTED;
   if (p.mode != kModeGeneric) {
     if (!aligned16(value) || !aligned16(out)) return MSDA_E_ALIGN;
     if (fused ? ((reinterpret_cast<uintptr_t>(offsets) & 7u) != 0) : ((reinterpret_cast<uintptr_t>(loc) & 7u) != 0))
@@ -143,6 +150,15 @@ int msda_b200_forward_bf16(const void* value, const int64_t* shapes, const int64
                         nullptr, 2);
 }
 
+int msda_b200_forward_f64(const double* value, const int64_t* shapes, const int64_t* lsi, const double* loc,
+                          const double* attn, int N, int S, int M, int D, int L, int Lq, int P, double* out,
+                          void* stream) {
+  if (!value || !shapes || !lsi || !loc || !attn || !out) return MSDA_E_NULLPTR;
+  int rc = check_dims(N, S, M, D, L, Lq, P, 8);
+  if (rc) return rc;
+  return launch_forward_f64(value, shapes, lsi, loc, attn, N, S, M, D, L, Lq, P, out, (cudaStream_t)stream);
+}
+
 int msda_b200_forward_f32_ex(const float* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
                              const float* attn, int N, int S, int M, int D, int L, int Lq, int P, float* out,
                              void* stream, const msda_b200_tuning_t* tuning) {
@@ -171,6 +187,22 @@ int msda_b200_forward_fused_bf16(const void* value, const int64_t* shapes, const
                                  int L, int Lq, int P, void* out, void* stream, const msda_b200_tuning_t* tuning) {
   return forward_common(value, shapes, lsi, nullptr, nullptr, ref, ref_dim, offsets, logits, N, S, M, D, L, Lq, P, out,
                         stream, tuning, 2);
+}
+
+int msda_b200_forward_fused_pitched_f32(const float* value, const int64_t* shapes, const int64_t* lsi, const float* ref,
+                                        int ref_dim, const float* offsets, int off_pitch, const float* logits,
+                                        int logit_pitch, int N, int S, int M, int D, int L, int Lq, int P, float* out,
+                                        void* stream, const msda_b200_tuning_t* tuning) {
+  return forward_common(value, shapes, lsi, nullptr, nullptr, ref, ref_dim, offsets, logits, N, S, M, D, L, Lq, P, out,
+                        stream, tuning, 4, off_pitch, logit_pitch);
+}
+
+int msda_b200_forward_fused_pitched_bf16(const void* value, const int64_t* shapes, const int64_t* lsi, const float* ref,
+                                         int ref_dim, const float* offsets, int off_pitch, const float* logits,
+                                         int logit_pitch, int N, int S, int M, int D, int L, int Lq, int P, void* out,
+                                         void* stream, const msda_b200_tuning_t* tuning) {
+  return forward_common(value, shapes, lsi, nullptr, nullptr, ref, ref_dim, offsets, logits, N, S, M, D, L, Lq, P, out,
+                        stream, tuning, 2, off_pitch, logit_pitch);
 }
 
 int msda_b200_locations_softmax_f32(const int64_t* shapes, const float* ref, int ref_dim, const float* offsets,

@@ -279,6 +279,68 @@ __global__ void __launch_bounds__(256) msda_fwd_generic_kernel(const FwdParams p
 }
 
 // -----------------------------------------------------------------------------------------------
+// float64 forward: the reference instantiates its kernel for double too (AT_DISPATCH_FLOATING_TYPES,
+// ms_deform_attn_cuda.cu:64).  Same loop as the generic kernel in double arithmetic with the contraction nvcc
+// applies to the reference's double expressions (DFMA), written out explicitly.  Not a performance path.
+// -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msda_fwd_generic_f64_kernel(const double* __restrict__ value,
+                                                                   const int64_t* __restrict__ shapes,
+                                                                   const int64_t* __restrict__ lsi,
+                                                                   const double* __restrict__ loc,
+                                                                   const double* __restrict__ attn, int N, int S, int M,
+                                                                   int D, int L, int Lq, int P, double* __restrict__ out) {
+  const long long total = (long long)N * Lq * M * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % D);
+    const long long unit = idx / D;
+    const int m = (int)(unit % M);
+    const long long b = unit / ((long long)M * Lq);
+    const double* vb = value + (size_t)b * S * M * D + (size_t)m * D + c;
+    const double* locp = loc + (size_t)unit * L * P * 2;
+    const double* attp = attn + (size_t)unit * L * P;
+    double acc = 0.0;
+    for (int l = 0; l < L; ++l) {
+      const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+      const double* vl = vb + (size_t)((int)lsi[l]) * M * D;
+      const ptrdiff_t cs = (ptrdiff_t)M * D, rs = (ptrdiff_t)W * M * D;
+      for (int pt = 0; pt < P; ++pt) {
+        const int s = l * P + pt;
+        const double h_im = __fma_rn(locp[2 * s + 1], (double)H, -0.5);
+        const double w_im = __fma_rn(locp[2 * s], (double)W, -0.5);
+        if (!(h_im > -1 && w_im > -1 && h_im < H && w_im < W)) continue;
+        const double hf = floor(h_im), wf = floor(w_im);
+        const int h_low = (int)hf, w_low = (int)wf;
+        const double lh = __dsub_rn(h_im, hf), lw = __dsub_rn(w_im, wf);
+        const double hh = __dsub_rn(1.0, lh), hw = __dsub_rn(1.0, lw);
+        const double w1 = __dmul_rn(hh, hw), w2 = __dmul_rn(hh, lw), w3 = __dmul_rn(lh, hw), w4 = __dmul_rn(lh, lw);
+        const ptrdiff_t o1 = ((ptrdiff_t)h_low * W + w_low) * cs;
+        const bool t = h_low >= 0, bt = h_low + 1 <= H - 1, lf = w_low >= 0, rt = w_low + 1 <= W - 1;
+        const double v1 = (t && lf) ? vl[o1] : 0.0, v2 = (t && rt) ? vl[o1 + cs] : 0.0;
+        const double v3 = (bt && lf) ? vl[o1 + rs] : 0.0, v4 = (bt && rt) ? vl[o1 + rs + cs] : 0.0;
+        double tt = __dmul_rn(w2, v2);
+        tt = __fma_rn(w1, v1, tt);
+        tt = __fma_rn(w3, v3, tt);
+        tt = __fma_rn(w4, v4, tt);
+        acc = __fma_rn(attp[s], tt, acc);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+int launch_forward_f64(const double* value, const int64_t* shapes, const int64_t* lsi, const double* loc,
+                       const double* attn, int N, int S, int M, int D, int L, int Lq, int P, double* out,
+                       cudaStream_t stream) {
+  const long long total = (long long)N * Lq * M * D;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  msda_fwd_generic_f64_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(value, shapes, lsi, loc, attn, N, S, M, D,
+                                                                                 L, Lq, P, out);
+  return (int)cudaGetLastError();
+}
+
+// -----------------------------------------------------------------------------------------------
 // Sampling-index dump (test/inspection): record layout == msda_b200_index_t == oracle's
 // -----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msda_sample_index_kernel(const float* __restrict__ loc,

@@ -205,13 +205,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
   constexpr int NL = LPT / PT;          // levels
   static_assert(D % VEC == 0 && LPR >= 1 && 32 % LPR == 0, "bad lane layout");
   static_assert(LPT % LPR == 0 && LPT % PT == 0 && SPL >= 1, "bad sample layout");
-  // Record slot of (sample s, lane group g): s*UPW + ((g + rot(s)) % UPW).  The rotation makes the phase-1
-  // STS.128 of a quarter-warp (8 lanes = 8 different (s,g)) hit 8 different 16-byte bank groups; without it
-  // lanes with equal g collide 4-way (ncu: 64 instead of 16 wavefronts per step).
-  auto slot = [](int s, int g) -> int {
-    const int rot = LPR == 8 ? (s >> 1) : s * (8 / LPR);
-    return s * UPW + ((g + rot) & (UPW - 1));
-  };
+  // Record slot of (sample s, lane group g): s*UPW + (g ^ swz(s)).  The XOR swizzle makes the phase-1 STS.128
+  // of a quarter-warp (8 lanes = 8 different (s,g)) hit 8 different 16-byte bank groups; without it lanes with
+  // equal g collide 4-way (ncu: 64 instead of 16 wavefronts per step).  swz(s) takes only 4 values, so phase 2
+  // keeps 4 pre-swizzled base pointers and every record read is LDS.128 [base_c + immediate].
+  auto swz = [](int s) -> int { return (LPR == 8 ? (s >> 1) : s * (8 / LPR)) & (UPW - 1); };
+  auto slot = [&](int s, int g) -> int { return s * UPW + (g ^ swz(s)); };
+  constexpr int kSwzStep = LPR == 8 ? 1 : 8 / LPR;      // swz(s) in {0,1,2,3} * kSwzStep
 
   __shared__ int sH[NL], sW[NL], sStart[NL], sTileCum[NL + 1];
   __shared__ float sHf[NL], sWf[NL];
@@ -249,6 +249,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
   const long long total_tiles = (long long)p.N * tiles_per_bm * M;
   const int chunks_per_warp = (p.tile_q + NW * UPW - 1) / (NW * UPW);   // warp steps per tile
   float4* sRec = sRecAll + (size_t)warp * LPT * UPW;
+  const float4* sRecG[4];                           // this lane group's record column under each swizzle value
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sRecG[c] = sRec + (g ^ ((c * kSwzStep) & (UPW - 1)));
   const float inv_p = 1.0f / (float)PT;
 
   // ---- work cursor: (tile, chunk) pairs of this warp, flattened so the next step can be prefetched ----
@@ -288,8 +291,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
 #pragma unroll
       for (int i = 0; i < SPL; ++i) {
         const int s = i * LPR + k;
-        pf.lg[i] = ld_stream_f1(p.logits + unit * LPT + s);
-        pf.off[i] = ld_stream_f2(p.offsets + (unit * LPT + s) * 2);
+        // rows of offsets / logits may be slices of one merged projection output (pitch > dense row length)
+        pf.lg[i] = ld_stream_f1(p.logits + bq * p.logit_pitch + t_m * LPT + s);
+        pf.off[i] = ld_stream_f2(p.offsets + bq * p.off_pitch + (t_m * LPT + s) * 2);
         const float* rp = p.ref + (bq * NL + s / PT) * p.ref_dim;
         if (p.ref_dim == 4) {
           pf.ref[i] = __ldg(reinterpret_cast<const float4*>(rp));
@@ -399,6 +403,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
     f32x2 acc[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) acc[j] = 0ull;
+    auto rec_at = [&](int s) -> float4 { return sRecG[(swz(s) / kSwzStep) & 3][s * UPW]; };
     // warp-uniform three-way split per sample:
     //   all 4 corners of all units valid -> plain loads, no zero-fill, no predicates                  (common)
     //   every unit out of range          -> nothing issued, nothing accumulated (cuh:288)              (borders)
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
     if constexpr (PD == 1) {
 #pragma unroll
       for (int s = 0; s < LPT; ++s) {
-        const float4 rc = sRec[slot(s, g)];
+        const float4 rc = rec_at(s);
         const int packed = __float_as_int(rc.x);
         const int mk = packed & 15;
         const char* c1 = vbase + (ptrdiff_t)(packed & ~15);
@@ -431,7 +436,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
       float4 rc[PD];
       bool live[PD];            // warp-uniform: at least one unit takes this sample
       auto issue = [&](int s, int d) {
-        rc[d] = sRec[slot(s, g)];
+        rc[d] = rec_at(s);
         const int packed = __float_as_int(rc[d].x);
         const int mk = packed & 15;
         const bool all_in = __all_sync(0xffffffffu, mk == 15);

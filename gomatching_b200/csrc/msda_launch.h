@@ -19,6 +19,7 @@ struct FwdParams {
   const float* offsets;       // (N,Lq,M,L,P,2)
   const float* logits;        // (N,Lq,M,L*P)
   int ref_dim;
+  int off_pitch, logit_pitch; // floats between consecutive (b,q) rows of offsets / logits (M*L*P*2 and M*L*P when dense)
   void* out;                  // (N,Lq,M*D)
   int N, S, M, D, L, Lq, P;
   // tiling (never changes results)
@@ -33,6 +34,9 @@ struct FwdParams {
 // Each returns a cudaError_t cast to int (0 = ok) or MSDA_E_UNSUPPORTED (-5).
 int launch_forward_f32(const FwdParams& p, cudaStream_t stream);
 int launch_forward_bf16(const FwdParams& p, cudaStream_t stream);
+int launch_forward_f64(const double* value, const int64_t* shapes, const int64_t* lsi, const double* loc,
+                       const double* attn, int N, int S, int M, int D, int L, int Lq, int P, double* out,
+                       cudaStream_t stream);
 int forward_variant_count();
 // compile-time-specialised kernels for the DeepSolo configuration (msda_forward_fast.cu)
 bool fast_supported(int D, int L, int P);

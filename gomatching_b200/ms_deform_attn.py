@@ -48,6 +48,8 @@ class MSDeformAttn(nn.Module):
         self.n_heads = n_heads
         self.n_points = n_points
         self.use_fused = True      # fused glue+sampler kernel when no gradient is needed
+        self.merge_query_projections = True   # inference: sampling_offsets || attention_weights as ONE 256->384 GEMM
+        self._qproj_cache = None
         self.tuning = None         # optional msda_b200_tuning_t fields (dict); never changes results
 
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
@@ -74,6 +76,18 @@ class MSDeformAttn(nn.Module):
         xavier_uniform_(self.output_proj.weight.data)
         constant_(self.output_proj.bias.data, 0.)
 
+    def _merged_query_projection(self):
+        """[W_offsets; W_attention] (384 x 256 for DeepSolo) and the merged bias, rebuilt only when a parameter changed."""
+        so, aw = self.sampling_offsets, self.attention_weights
+        key = (so.weight._version, so.bias._version, aw.weight._version, aw.bias._version, so.weight.data_ptr(),
+               aw.weight.data_ptr(), so.weight.device, so.weight.dtype)
+        if self._qproj_cache is None or self._qproj_cache[0] != key:
+            with torch.no_grad():
+                w = torch.cat([so.weight, aw.weight], 0).contiguous()
+                b = torch.cat([so.bias, aw.bias], 0).contiguous()
+            self._qproj_cache = (key, w, b)
+        return self._qproj_cache[1], self._qproj_cache[2]
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
         """
@@ -99,17 +113,28 @@ class MSDeformAttn(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, M, D)
-        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
-        attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
+        needs_grad = torch.is_grad_enabled() and (
+            query.requires_grad or input_flatten.requires_grad or reference_points.requires_grad
+            or any(p.requires_grad for p in self.parameters()))
+        fused_ok = (self.use_fused and not needs_grad and value.is_cuda
+                    and value.dtype in (torch.float32, torch.bfloat16) and fused_supported(value.dtype, D, L, P))
+        if fused_ok and self.merge_query_projections:
+            # both projections read the same `query` (ms_deform_attn.py:137-138): one GEMM, and the fused kernel
+            # takes the two column slices of its output as row-pitched views -- no copy, no second pass over query
+            w, b = self._merged_query_projection()
+            qp = F.linear(query, w, b)
+            n_off = M * L * P * 2
+            sampling_offsets = qp[..., :n_off].view(N, Len_q, M, L, P, 2)
+            attention_weights = qp[..., n_off:].view(N, Len_q, M, L * P)
+        else:
+            sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
+            attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
 
-        needs_grad = torch.is_grad_enabled() and (value.requires_grad or sampling_offsets.requires_grad
-                                                  or attention_weights.requires_grad or reference_points.requires_grad)
-        if (self.use_fused and not needs_grad and value.is_cuda and value.dtype in (torch.float32, torch.bfloat16)
-                and fused_supported(value.dtype, D, L, P)):
+        if fused_ok:
             output = ms_deform_attn_forward_fused(
                 value.contiguous(), input_spatial_shapes, input_level_start_index,
-                reference_points.float().contiguous(), sampling_offsets.float().contiguous(),
-                attention_weights.float().contiguous(), tuning=self.tuning)
+                reference_points.float().contiguous(), sampling_offsets.float(), attention_weights.float(),
+                tuning=self.tuning)
         else:
             attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
             if reference_points.shape[-1] == 2:

@@ -61,12 +61,22 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     _check_im2col_step(N, im2col_step)
     lib = _native.lib()
+    if value.dtype == torch.float64:        # the reference dispatches double too (ms_deform_attn_cuda.cu:64)
+        loc64 = sampling_loc.double().contiguous()
+        attn64 = attn_weight.double().contiguous()
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        with torch.cuda.device(value.device):
+            rc = lib.msda_b200_forward_f64(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                           loc64.data_ptr(), attn64.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "ms_deform_attn_forward")
+        return out
     if value.dtype == torch.float32:
         fn = lib.msda_b200_forward_f32_ex
     elif value.dtype == torch.bfloat16:
         fn = lib.msda_b200_forward_bf16_ex
     else:
-        raise RuntimeError("msda_b200: value dtype %s has no kernel (float32 and bfloat16 are implemented)" % value.dtype)
+        raise RuntimeError("msda_b200: value dtype %s has no kernel (float32, float64, bfloat16 are implemented)" % value.dtype)
     loc = sampling_loc if sampling_loc.dtype == torch.float32 else sampling_loc.float()
     attn = attn_weight if attn_weight.dtype == torch.float32 else attn_weight.float()
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
@@ -78,6 +88,22 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def _row_pitch(t, row_len):
+    """Floats between consecutive (b,q) rows if ``t`` is a dense-row view (e.g. a column slice of a wider projection
+    output), else None."""
+    flat_ok = t.stride(-1) == 1
+    inner = 1
+    for d in range(t.dim() - 1, 1, -1):                    # dims after (N, Lq) must be dense
+        flat_ok = flat_ok and (t.shape[d] == 1 or t.stride(d) == inner)
+        inner *= t.shape[d]
+    if not flat_ok or inner != row_len:
+        return None
+    pitch = t.stride(1) if t.shape[1] > 1 else row_len
+    if pitch < row_len or (t.shape[0] > 1 and t.stride(0) != pitch * t.shape[1]):
+        return None
+    return pitch
+
+
 def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
                                  attention_logits, n_points=None, tuning=None):
     """softmax(logits) + offsets->locations + sampling + weighted reduction in one kernel.
@@ -87,12 +113,21 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
     ms_deform_attn.py:137-152 without materialising sampling_locations / attention_weights.
     """
     _require(value.is_cuda, "Not implemented on the CPU")
-    for t, name in ((value, "value"), (reference_points, "reference_points"), (sampling_offsets, "sampling_offsets"),
-                    (attention_logits, "attention_logits"), (spatial_shapes, "spatial_shapes"),
+    for t, name in ((value, "value"), (reference_points, "reference_points"), (spatial_shapes, "spatial_shapes"),
                     (level_start_index, "level_start_index")):
         _require(t.is_cuda and t.is_contiguous(), "%s tensor has to be a contiguous CUDA tensor" % name)
+    _require(sampling_offsets.is_cuda and attention_logits.is_cuda, "offsets / logits must be CUDA tensors")
     N, S, M, D = value.shape
     N2, Lq, M2, L, P, two = sampling_offsets.shape
+    attention_logits = attention_logits.reshape(N, Lq, M, L * P) if attention_logits.dim() != 4 else attention_logits
+    # dense, or row-pitched views of one merged projection output (no copy); anything else is made contiguous
+    off_pitch = _row_pitch(sampling_offsets, M * L * P * 2)
+    lg_pitch = _row_pitch(attention_logits, M * L * P)
+    pitched = (off_pitch is not None and lg_pitch is not None and (off_pitch != M * L * P * 2 or lg_pitch != M * L * P)
+               and D == 32 and L == 4 and P == 4 and off_pitch % 2 == 0 and sampling_offsets.data_ptr() % 8 == 0)
+    if not pitched:
+        sampling_offsets = sampling_offsets.contiguous()
+        attention_logits = attention_logits.contiguous()
     _require((N2, M2, two) == (N, M, 2), "sampling_offsets shape does not match value")
     ref_dim = reference_points.shape[-1]
     if ref_dim not in (2, 4):
@@ -102,18 +137,23 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
     _require(reference_points.dtype == torch.float32 and sampling_offsets.dtype == torch.float32
              and attention_logits.dtype == torch.float32, "reference_points / offsets / logits must be float32")
     lib = _native.lib()
-    if value.dtype == torch.float32:
-        fn = lib.msda_b200_forward_fused_f32
-    elif value.dtype == torch.bfloat16:
-        fn = lib.msda_b200_forward_fused_bf16
-    else:
+    if value.dtype not in (torch.float32, torch.bfloat16):
         raise RuntimeError("msda_b200: value dtype %s has no kernel" % value.dtype)
+    f32 = value.dtype == torch.float32
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream
-        rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
-                ref_dim, sampling_offsets.data_ptr(), attention_logits.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(),
-                stream, _native.make_tuning(tuning))
+        if pitched:
+            fn = lib.msda_b200_forward_fused_pitched_f32 if f32 else lib.msda_b200_forward_fused_pitched_bf16
+            rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                    reference_points.data_ptr(), ref_dim, sampling_offsets.data_ptr(), off_pitch,
+                    attention_logits.data_ptr(), lg_pitch, N, S, M, D, L, Lq, P, out.data_ptr(), stream,
+                    _native.make_tuning(tuning))
+        else:
+            fn = lib.msda_b200_forward_fused_f32 if f32 else lib.msda_b200_forward_fused_bf16
+            rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                    reference_points.data_ptr(), ref_dim, sampling_offsets.data_ptr(), attention_logits.data_ptr(), N, S,
+                    M, D, L, Lq, P, out.data_ptr(), stream, _native.make_tuning(tuning))
     _native.check(rc, "ms_deform_attn_forward_fused")
     return out
 

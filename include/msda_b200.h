@@ -88,6 +88,13 @@ int msda_b200_forward_bf16(const void* value_bf16, const int64_t* shapes, const 
                            int N, int S, int M, int D, int L, int Lq, int P,
                            void* out_bf16, void* stream);
 
+/* float64, as the reference's AT_DISPATCH_FLOATING_TYPES also instantiates (ms_deform_attn_cuda.cu:64); a plain
+ * one-thread-per-element kernel in double arithmetic -- completeness, not a performance path */
+int msda_b200_forward_f64(const double* value, const int64_t* shapes, const int64_t* lsi,
+                          const double* loc, const double* attn,
+                          int N, int S, int M, int D, int L, int Lq, int P,
+                          double* out, void* stream);
+
 /* same two with explicit tuning (used by bench.py and the tests to pin a variant) */
 int msda_b200_forward_f32_ex(const float* value, const int64_t* shapes, const int64_t* lsi,
                              const float* loc, const float* attn,
@@ -113,6 +120,21 @@ int msda_b200_forward_fused_bf16(const void* value_bf16, const int64_t* shapes, 
                                  const float* ref, int ref_dim, const float* offsets, const float* logits,
                                  int N, int S, int M, int D, int L, int Lq, int P,
                                  void* out_bf16, void* stream, const msda_b200_tuning_t* tuning);
+
+/* same, with offsets / logits given as row-pitched views: row (b,q) of offsets starts at offsets + (b*Lq+q)*off_pitch
+ * floats (M*L*P*2 used), of logits at logits + (b*Lq+q)*logit_pitch (M*L*P used).  Lets the caller compute both
+ * projections of `query` (ms_deform_attn.py:137-138) as ONE 256->384 GEMM and hand over the two column slices
+ * without a copy.  Only the DeepSolo-shape kernels (D=32, L=4, P=4) take pitches; otherwise MSDA_E_UNSUPPORTED. */
+int msda_b200_forward_fused_pitched_f32(const float* value, const int64_t* shapes, const int64_t* lsi,
+                                        const float* ref, int ref_dim, const float* offsets, int off_pitch,
+                                        const float* logits, int logit_pitch,
+                                        int N, int S, int M, int D, int L, int Lq, int P,
+                                        float* out, void* stream, const msda_b200_tuning_t* tuning);
+int msda_b200_forward_fused_pitched_bf16(const void* value_bf16, const int64_t* shapes, const int64_t* lsi,
+                                         const float* ref, int ref_dim, const float* offsets, int off_pitch,
+                                         const float* logits, int logit_pitch,
+                                         int N, int S, int M, int D, int L, int Lq, int P,
+                                         void* out_bf16, void* stream, const msda_b200_tuning_t* tuning);
 
 /* ---- glue kernels on their own (what the fused kernel does in registers), for tests/inspection ---- */
 /* loc_out (N,Lq,M,L,P,2), attn_out (N,Lq,M,L,P); either output may be NULL.  lanes_per_unit selects the

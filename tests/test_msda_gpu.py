@@ -61,6 +61,17 @@ def test_core_fp32_bit_exact_vs_oracle_and_in_tolerance_vs_reference(core_cases,
     assert rel_err(out, c["out_f64"]) <= 1e-4
 
 
+@pytest.mark.parametrize("name", CORE)
+def test_core_fp64_bit_exact_vs_oracle(core_cases, name):
+    """The reference also instantiates double (ms_deform_attn_cuda.cu:64)."""
+    import gomatching_b200 as g
+    c = core_cases.case(name)
+    out = g.ms_deform_attn_forward(dev(c["value"]).double(), dev(c["shapes"]), dev(c["lsi"]), dev(c["loc"]).double(),
+                                   dev(c["attn"]).double(), 64).cpu().numpy()
+    assert np.array_equal(out, O.forward_f64(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"]))
+    assert rel_err(out, c["out_f64"]) <= 1e-12
+
+
 @pytest.mark.parametrize("name", ["uniform_d32", "edges_d32", "d64_p8"])
 def test_every_variant_and_mode_gives_identical_bits(core_cases, name):
     from gomatching_b200 import _native
@@ -446,3 +457,44 @@ def test_nccl_gather_of_frame_records_two_gpus(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True,
                        text=True, cwd=ROOT, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_pitched_fused_call_equals_dense(core_cases):
+    """offsets / logits as column slices of one merged 256->384 projection output (no copy)."""
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("decoder", 360, 640, n=2, seed=12, dist="local")
+    N, S, M, D, L, Lq, P = w.dims
+    v, sh, ls, rf = dev(w.value), dev(w.shapes), dev(w.lsi), dev(w.ref)
+    dense = g.ms_deform_attn_forward_fused(v, sh, ls, rf, dev(w.offsets), dev(w.logits))
+    merged = torch.cat([w.offsets.view(N, Lq, -1), w.logits.view(N, Lq, -1)], -1).cuda()       # (N, Lq, 384)
+    off_view = merged[..., :M * L * P * 2].view(N, Lq, M, L, P, 2)
+    lg_view = merged[..., M * L * P * 2:].view(N, Lq, M, L * P)
+    assert not off_view.is_contiguous() and not lg_view.is_contiguous()
+    assert torch.equal(g.ms_deform_attn_forward_fused(v, sh, ls, rf, off_view, lg_view), dense)
+    # bf16 storage too
+    vb = v.to(torch.bfloat16)
+    assert torch.equal(g.ms_deform_attn_forward_fused(vb, sh, ls, rf, off_view, lg_view),
+                       g.ms_deform_attn_forward_fused(vb, sh, ls, rf, dev(w.offsets), dev(w.logits)))
+
+
+def test_module_merged_projection_matches_separate_projections(module_cases):
+    import gomatching_b200 as g
+    c = module_cases.case("ref2_mask")
+    mod = g.MSDeformAttn(256, 4, 8, 4)
+    mod.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("sd/")}, strict=True)
+    mod = mod.cuda().eval()
+    args = (dev(c["query"]), dev(c["ref"]), dev(c["src"]), dev(c["shapes"]), dev(c["lsi"]), dev(c["mask"]))
+    with torch.no_grad():
+        a = mod(*args)
+        mod.merge_query_projections = False
+        b = mod(*args)
+        # the cache follows in-place parameter updates
+        mod.merge_query_projections = True
+        mod.sampling_offsets.bias.add_(0.25)
+        c2 = mod(*args)
+        mod.merge_query_projections = False
+        d2 = mod(*args)
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+    assert rel_err(c2.cpu().numpy(), d2.cpu().numpy()) <= 1e-5
+    assert rel_err(a.cpu().numpy(), c2.cpu().numpy()) > 1e-4
