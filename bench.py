@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per step per GPU")
-    ap.add_argument("--dist", default="local", choices=["local", "uniform"])
+    ap.add_argument("--dist", default="local", choices=["local", "uniform", "oor", "center"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="time the core operator (loc/attn precomputed)")

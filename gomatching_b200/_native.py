@@ -124,6 +124,8 @@ def make_tuning(tuning) -> "ctypes.POINTER(Tuning) | None":
     for k, v in dict(tuning).items():
         if k == "force_v1":            # reserved[0] = 1: run the runtime-L*P tiled kernel instead of the specialised one
             t.reserved[0] = int(v)
+        elif k == "walk":              # reserved[1] = 1: contiguous raster tile walk per CTA (diagnostic) instead of the strided one
+            t.reserved[1] = int(v)
         else:
             setattr(t, k, int(v))
     return ctypes.pointer(t)

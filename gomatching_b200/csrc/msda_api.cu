@@ -46,23 +46,25 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
   if (sms < 0) return sms;
   const bool can_tile = tiled_supported(elem_bytes, p.D, p.L, p.P, fused);
   int mode = tn ? tn->mode : 0;
-  if (mode == 0) mode = !can_tile ? kModeGeneric : (p.Lq == p.S ? kModePyramid : kModeLinear);
-  if (mode == kModePyramid && p.Lq != p.S) mode = kModeLinear;
+  const bool self_attn = p.Lq == p.S;
+  // defaults from the B200 sweeps (profiles/r01_sweep_s4_*.log): 2-D pyramid tiles only pay for the fp32 core
+  // operator in encoder self-attention; everything else runs linear query tiles
+  if (mode == 0) mode = !can_tile ? kModeGeneric : ((self_attn && elem_bytes == 4 && !fused) ? kModePyramid : kModeLinear);
+  if (mode == kModePyramid && !self_attn) mode = kModeLinear;
   if (mode != kModeGeneric && !can_tile) {
     if (fused) return MSDA_E_UNSUPPORTED;
     mode = kModeGeneric;
   }
   if (mode == kModeGeneric && fused) return MSDA_E_UNSUPPORTED;
   p.mode = mode;
-  // defaults from the B200 sweeps (profiles/r01_sweep_*): encoder = pyramid 16x16 tiles with 16-warp CTAs,
-  // everything else = 64-query linear tiles with 8-warp CTAs
-  p.variant = tn ? tn->variant : (mode == kModePyramid ? 0 : 1);
+  p.variant = (tn && tn->variant >= 0 && (tn->mode || tn->variant)) ? tn->variant : 3;   // VB16, 8 warps, 4 CTAs/SM, 16-B records
   p.force_v1 = (tn && tn->reserved[0] == 1) ? 1 : 0;
-  if (p.variant < 0 || p.variant >= forward_variant_count()) p.variant = 0;
+  p.walk = (tn && tn->reserved[1] == 1) ? 1 : 0;
+  if (p.variant < 0 || p.variant >= forward_variant_count()) p.variant = 3;
   int th = (tn && tn->tile_h > 0) ? tn->tile_h : 16;
-  int tw = (tn && tn->tile_w > 0) ? tn->tile_w : 16;
-  int tq = (tn && tn->tile_q > 0) ? tn->tile_q : 64;
-  int cps = (tn && tn->ctas_per_sm > 0) ? tn->ctas_per_sm : 4;
+  int tw = (tn && tn->tile_w > 0) ? tn->tile_w : 8;
+  int tq = (tn && tn->tile_q > 0) ? tn->tile_q : ((self_attn && elem_bytes == 2) ? 256 : 64);
+  int cps = (tn && tn->ctas_per_sm > 0) ? tn->ctas_per_sm : (mode == kModePyramid ? 3 : 4);
   p.tile_w_log2 = ilog2_floor(tw < 4 ? 4 : tw);
   p.tile_h = th;
   p.tile_q = (mode == kModePyramid) ? th * (1 << p.tile_w_log2) : tq;
@@ -98,10 +100,10 @@ int forward_common(const void* value, const int64_t* shapes, const int64_t* lsi,
   p.logit_pitch = logit_pitch > 0 ? logit_pitch : M * L * P;
   if (p.off_pitch < M * L * P * 2 || p.logit_pitch < M * L * P || (p.off_pitch & 1)) return MSDA_E_DIMS;
   const bool pitched = fused && (p.off_pitch != M * L * P * 2 || p.logit_pitch != M * L * P);
-  if (pitched && !fast_supported(D, L, P)) return MSDA_E_UNSUPPORTED;   // only the specialised kernels take pitches
+  if (pitched && !fast_shape_supported(D, L, P)) return MSDA_E_UNSUPPORTED;   // only the specialised kernels take pitches
   rc = plan(p, elem_bytes, fused, tn);
   if (rc) return rc;
-  if (pitched && (p.mode == kModeGeneric || p.force_v1)) return MSDA_E_UNSUPPORTED;
+  if (pitched && (p.mode == kModeGeneric || p.force_v1 || !fast_supported(p))) return MSDA_E_UNSUPPORTED;
   if (p.mode != kModeGeneric) {
     if (!aligned16(value) || !aligned16(out)) return MSDA_E_ALIGN;
     if (fused ? ((reinterpret_cast<uintptr_t>(offsets) & 7u) != 0) : ((reinterpret_cast<uintptr_t>(loc) & 7u) != 0))

@@ -452,7 +452,7 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
     return (int)cudaGetLastError();
   }
   const int LP = p.L * p.P;
-  if (fast_supported(p.D, p.L, p.P) && !p.force_v1)
+  if (fast_supported(p) && !p.force_v1)
     return sizeof(T) == 4 ? launch_forward_fast_f32(p, stream) : launch_forward_fast_bf16(p, stream);
   if (p.D == 32) {
     if (!fused) return dispatch_variant<T, 32, 0>(p, stream);
@@ -471,7 +471,7 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int forward_variant_count() { return 10; }
+int forward_variant_count() { return fast_variant_count(); }
 
 bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused) {
   if (D != 32 && D != 64) return false;

@@ -1,26 +1,31 @@
 // Fast forward kernels for the DeepSolo configuration (L*P = 16, P = 4 known at compile time, D = 32).
 //
 // Same two-phase scheme as msda_forward.cu (phase 1: per-sample records computed once per unit and parked in
-// shared memory; phase 2: gather + weighted reduction), re-cut from what ncu and the gather microbenchmark
-// (tools/ubench/gather_bw.cu, profiles/r01_ubench_gather_v2.log) showed on B200:
+// shared memory; phase 2: gather + weighted reduction), re-cut from what the B200 measurements showed
+// (tools/ubench/*.cu, profiles/r01_ubench_*.log, profiles/r01_diag_*.log):
 //
-//   * 128-bit accesses -- LDG.128 and LDS.128 alike -- top out at ~62 B/clk/SM; LDG.E.256 (new on sm_100a)
-//     reaches 122 B/clk/SM on L1 hits and 73 B/clk/SM from L2.  So the gather uses 256-bit loads (VB = 32: 4
-//     lanes cover a 128-byte fp32 row, a warp gathers 8 rows per instruction) and the value rows are NOT staged
-//     in shared memory: an LDS.128 gather would be half as fast as LDG.256 through L1.
-//   * with every sample out of range (no gather at all) the previous revision still took 60 % of its normal
-//     time: it was instruction-issue bound.  Hence (a) packed fp32x2 arithmetic (FFMA2/FMUL2/FADD2, sm_100a;
-//     same IEEE rounding per element, so results stay bit-identical to the reference's FMA chain) -- 20 FP
-//     instructions per 8-unit step instead of 40; (b) a warp-uniform three-way split per sample step:
-//       all 4 corners of all units valid  -> plain loads, no zero-fill, no predicates            (common)
-//       every unit out of range           -> step skipped                                          (borders)
-//       otherwise                         -> zero-filled, predicated loads                         (rare)
-//     (c) L*P, P and the pixel pitch M*D*sizeof(T) are template constants: unrolled sample loop, the
-//     horizontal-neighbour offset is an immediate of the load.
+//   * the gather is bounded by the SM's L1 data path at ONE 128-byte wavefront per clock (LDG.128, LDG.256,
+//     LDS.128 and LDSM all top out at 0.97-1.0 rows/clk/SM) -- 66 k clocks per 720p encoder call -- and the
+//     previous revision spent as many clocks just ISSUING instructions: 329 warp instructions per unit, 203 us of
+//     its 500 us per 8-frame launch with every sample out of range (no gather at all).  This revision is on an
+//     instruction diet:
+//       - phase 1 does everything that depends only on the sample: the four bilinear weights (rows / columns
+//         that fall outside the map get weight 0, exactly the reference's zero padding), the byte offset of the
+//         top-left corner clamped into the map, and the distances dx / dy to the right / lower neighbour (0 at
+//         the border, so a clamped corner re-reads a valid pixel with weight 0).  A record is two float4:
+//         {offset, dy, attention, dx} and {w1, w2, w3, w4};
+//       - phase 2 is straight-line: per sample 2 LDS.128, 4 pointer adds, 4 unconditional loads and the
+//         reference's FMA chain in packed fp32x2 -- no masks, no predicates, no votes, no branches, so ptxas is
+//         free to keep the loads of the next samples in flight across the arithmetic of the current one
+//         (an L1 miss costs ~800 clocks under load; the gather needs ~1000 rows in flight per SM);
+//       - a lane owns CONTIGUOUS samples (lane k of a unit: samples k*SPL .. k*SPL+SPL-1, i.e. one level), so its
+//         phase-1 operands are one 256-bit + one 128-bit streaming load instead of eight scalar ones, and the
+//         fused kernel needs one reference point per lane.
+//   * packed fp32x2 arithmetic (FFMA2/FMUL2): same IEEE rounding per element as the reference's scalar chain,
+//     so outputs stay bit-identical to the reference kernel for finite inputs.  (0 * v stands in for the
+//     reference's skipped corner: identical unless v is Inf/NaN at a clamped border pixel.)
 //   * the next step's loc/attn (or offsets/logits/reference points) are prefetched into registers before the
 //     current step's gather starts, so their DRAM latency hides behind the gather.
-//   * LDG.256 destination registers are pure asm outputs: a read-write ("+r") operand made nvcc wrap the load
-//     in MOVs that wait for it (ncu source view), serialising the gather.
 #include "msda_device.cuh"
 #include "msda_launch.h"
 #include "../../include/msda_b200.h"
@@ -47,11 +52,6 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 
 // ---- a VB-byte slice of a value row held in registers ------------------------------------------------
 template <int VB> struct RowVec;
@@ -60,25 +60,12 @@ template <> struct RowVec<16> {
   __device__ __forceinline__ void load(const void* p) {
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
   }
-  __device__ __forceinline__ void load_or_zero(const void* p, bool pred) {
-    asm volatile(
-        "{\n .reg .pred pq;\n setp.ne.u32 pq, %5, 0;\n"
-        " mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0; mov.u32 %3, 0;\n"
-        " @pq ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
-        : "=&r"(a.x), "=&r"(a.y), "=&r"(a.z), "=&r"(a.w)
-        : "l"(p), "r"((uint32_t)pred));
+  // loads only if pred != 0; otherwise the registers keep their (finite) contents and nothing is written back
+  __device__ __forceinline__ void load_if(const void* p, uint32_t pred) {
+    asm volatile("{\n .reg .pred pq;\n setp.ne.u32 pq, %5, 0;\n @pq ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
+                 : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w) : "l"(p), "r"(pred));
   }
-  // pred: this lane loads; nofill (warp-uniform): every lane of the warp loads, so the zero-fill is branched over
-  __device__ __forceinline__ void load_sel(const void* p, bool pred, bool nofill) {
-    asm volatile(
-        "{\n .reg .pred pq, pf;\n setp.ne.u32 pq, %5, 0;\n setp.ne.u32 pf, %6, 0;\n"
-        " @pf bra.uni FILLED;\n"
-        " mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0; mov.u32 %3, 0;\n"
-        "FILLED:\n"
-        " @pq ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
-        : "=&r"(a.x), "=&r"(a.y), "=&r"(a.z), "=&r"(a.w)
-        : "l"(p), "r"((uint32_t)pred), "r"((uint32_t)nofill));
-  }
+  __device__ __forceinline__ void zero() { a = make_uint4(0, 0, 0, 0); }
   __device__ __forceinline__ uint32_t word(int i) const { return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w; }
 };
 template <> struct RowVec<32> {
@@ -88,26 +75,12 @@ template <> struct RowVec<32> {
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));
   }
-  __device__ __forceinline__ void load_or_zero(const void* p, bool pred) {
-    asm volatile(
-        "{\n .reg .pred pq;\n setp.ne.u32 pq, %9, 0;\n"
-        " mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0; mov.u32 %3, 0;\n"
-        " mov.u32 %4, 0; mov.u32 %5, 0; mov.u32 %6, 0; mov.u32 %7, 0;\n"
-        " @pq ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n}"
-        : "=&r"(lo.x), "=&r"(lo.y), "=&r"(lo.z), "=&r"(lo.w), "=&r"(hi.x), "=&r"(hi.y), "=&r"(hi.z), "=&r"(hi.w)
-        : "l"(p), "r"((uint32_t)pred));
+  __device__ __forceinline__ void load_if(const void* p, uint32_t pred) {
+    asm volatile("{\n .reg .pred pq;\n setp.ne.u32 pq, %9, 0;\n @pq ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n}"
+                 : "+r"(lo.x), "+r"(lo.y), "+r"(lo.z), "+r"(lo.w), "+r"(hi.x), "+r"(hi.y), "+r"(hi.z), "+r"(hi.w)
+                 : "l"(p), "r"(pred));
   }
-  __device__ __forceinline__ void load_sel(const void* p, bool pred, bool nofill) {
-    asm volatile(
-        "{\n .reg .pred pq, pf;\n setp.ne.u32 pq, %9, 0;\n setp.ne.u32 pf, %10, 0;\n"
-        " @pf bra.uni FILLED;\n"
-        " mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0; mov.u32 %3, 0;\n"
-        " mov.u32 %4, 0; mov.u32 %5, 0; mov.u32 %6, 0; mov.u32 %7, 0;\n"
-        "FILLED:\n"
-        " @pq ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n}"
-        : "=&r"(lo.x), "=&r"(lo.y), "=&r"(lo.z), "=&r"(lo.w), "=&r"(hi.x), "=&r"(hi.y), "=&r"(hi.z), "=&r"(hi.w)
-        : "l"(p), "r"((uint32_t)pred), "r"((uint32_t)nofill));
-  }
+  __device__ __forceinline__ void zero() { lo = make_uint4(0, 0, 0, 0); hi = lo; }
   __device__ __forceinline__ uint32_t word(int i) const {
     return i == 0 ? lo.x : i == 1 ? lo.y : i == 2 ? lo.z : i == 3 ? lo.w : i == 4 ? hi.x : i == 5 ? hi.y : i == 6 ? hi.z : hi.w;
   }
@@ -147,24 +120,38 @@ __device__ __forceinline__ void store_row(void* p, const f32x2 (&acc)[NP]) {
   }
 }
 
+// N consecutive floats of a streamed-once operand (N = 2, 4, 8), one vector load, no L1 allocation, L2 evict-first
+template <int N>
+__device__ __forceinline__ void ld_stream_vec(const float* p, float (&f)[N]) {
+  static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16, "vector width");
+  if constexpr (N == 1) {
+    f[0] = ld_stream_f1(p);
+  } else if constexpr (N == 2) {
+    const float2 r = ld_stream_f2(p);
+    f[0] = r.x; f[1] = r.y;
+  } else if constexpr (N == 4) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "l"(p), "l"(l2_evict_first_policy()));
+  } else if constexpr (N == 8) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+                 : "l"(p), "l"(l2_evict_first_policy()));
+  } else {
+    float lo[8], hi[8];
+    ld_stream_vec<8>(p, lo);
+    ld_stream_vec<8>(p + 8, hi);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { f[i] = lo[i]; f[8 + i] = hi[i]; }
+  }
+}
+
 // The reference's arithmetic for one sample, two channels at a time (cuh:80-82, :290):
-//   w1=hh*hw w2=hh*lw w3=lh*hw w4=lh*lw ; val = FMUL(w2,v2) -> FFMA(w1,v1,.) -> FFMA(w3,v3,.) -> FFMA(w4,v4,.)
-//   acc = FFMA(attn, val, acc).  Each packed instruction rounds its two elements exactly like the scalar one.
+//   val = FMUL(w2,v2) -> FFMA(w1,v1,.) -> FFMA(w3,v3,.) -> FFMA(w4,v4,.) ; acc = FFMA(attn, val, acc).
+// Each packed instruction rounds its two elements exactly like the scalar one.
 template <typename T, int VB, int NP>
-__device__ __forceinline__ void accumulate_sample(f32x2 (&acc)[NP], const float4& rc, const RowVec<VB>& q1,
+__device__ __forceinline__ void accumulate_sample(f32x2 (&acc)[NP], const float4& w, float attn, const RowVec<VB>& q1,
                                                   const RowVec<VB>& q2, const RowVec<VB>& q3, const RowVec<VB>& q4) {
-  const float lh = rc.y, lw = rc.z;
-  const f32x2 one = pk(1.0f, 1.0f);
-  const f32x2 h2 = sub2(one, pk(lh, lw));          // {hh, hw}
-  float hh, hw;
-  upk(h2, hh, hw);
-  const f32x2 cw = pk(hw, lw);                     // {hw, lw}
-  const f32x2 wtop = mul2(pk(hh, hh), cw);         // {w1, w2}
-  const f32x2 wbot = mul2(pk(lh, lh), cw);         // {w3, w4}
-  float w1, w2, w3, w4;
-  upk(wtop, w1, w2);
-  upk(wbot, w3, w4);
-  const f32x2 W1 = pk(w1, w1), W2 = pk(w2, w2), W3 = pk(w3, w3), W4 = pk(w4, w4), A = pk(rc.w, rc.w);
+  const f32x2 W1 = pk(w.x, w.x), W2 = pk(w.y, w.y), W3 = pk(w.z, w.z), W4 = pk(w.w, w.w), A = pk(attn, attn);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     f32x2 t = mul2(W2, chan_pair<T, VB>(q2, j));
@@ -175,47 +162,45 @@ __device__ __forceinline__ void accumulate_sample(f32x2 (&acc)[NP], const float4
   }
 }
 
-// Raw operands of one unit's samples held by one lane between the prefetch and phase 1.
-template <int SPL, bool FUSED> struct Prefetched;
-template <int SPL> struct Prefetched<SPL, false> {
-  float2 xy[SPL];
+// Raw operands of one lane's SPL samples between the prefetch and phase 1.
+template <int SPL, int NLV, bool FUSED> struct Prefetched;
+template <int SPL, int NLV> struct Prefetched<SPL, NLV, false> {
+  float xy[2 * SPL];
   float a[SPL];
 };
-template <int SPL> struct Prefetched<SPL, true> {
-  float2 off[SPL];
+template <int SPL, int NLV> struct Prefetched<SPL, NLV, true> {
+  float off[2 * SPL];
   float lg[SPL];
-  float4 ref[SPL];
+  float4 ref[NLV];
 };
 
 //   T     float | __nv_bfloat16 storage of value/out (arithmetic fp32)
 //   VB    bytes of a value row one lane loads (32: LDG.E.256, 16: LDG.E.128)
-//   LPT   L*P, PT = P (compile time) ; CSB = M*D*sizeof(T) if known at compile time else 0
+//   LPT   L*P, PT = P (compile time)
 //   NW    warps per CTA ; MINB min CTAs per SM (register budget)
-//   PD    gather pipeline depth: the corner loads of sample s+PD-1 are issued before sample s is consumed, so a
-//         warp keeps 4*(PD-1)..4*PD row loads in flight (ncu: with PD=1 the kernel is latency-bound -- almost
-//         every step waits for an L2 round trip because one of its 32 rows misses L1)
-template <typename T, int D, int VB, int LPT, int PT, int CSB, bool FUSED, int NW, int MINB, int PD>
+//   PD    gather pipeline depth in SOURCE order: the corner loads of sample s+PD-1 are issued before sample s is
+//         consumed (ptxas may hoist further: the sample loop is branch-free)
+template <typename T, int D, int VB, int LPT, int PT, bool FUSED, int NW, int MINB, int PD, bool REC16>
 __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdParams p) {
   constexpr int EB = (int)sizeof(T);
   constexpr int VEC = VB / EB;          // channels per lane
   constexpr int NP = VEC / 2;           // channel pairs per lane
-  constexpr int LPR = D / VEC;          // lanes per value row
+  constexpr int LPR = D / VEC;          // lanes per value row = lanes per unit
   constexpr int UPW = 32 / LPR;         // units per warp step
-  constexpr int SPL = LPT / LPR;        // samples per lane in phase 1
+  constexpr int SPL = LPT / LPR;        // samples per lane in phase 1 (contiguous: k*SPL ..)
   constexpr int NL = LPT / PT;          // levels
-  static_assert(D % VEC == 0 && LPR >= 1 && 32 % LPR == 0, "bad lane layout");
+  constexpr int NLV = SPL > PT ? SPL / PT : 1;   // levels one lane's samples span
+  static_assert(D % VEC == 0 && LPR >= 2 && LPR <= 8 && 32 % LPR == 0, "bad lane layout");
   static_assert(LPT % LPR == 0 && LPT % PT == 0 && SPL >= 1, "bad sample layout");
-  // Record slot of (sample s, lane group g): s*UPW + (g ^ swz(s)).  The XOR swizzle makes the phase-1 STS.128
-  // of a quarter-warp (8 lanes = 8 different (s,g)) hit 8 different 16-byte bank groups; without it lanes with
-  // equal g collide 4-way (ncu: 64 instead of 16 wavefronts per step).  swz(s) takes only 4 values, so phase 2
-  // keeps 4 pre-swizzled base pointers and every record read is LDS.128 [base_c + immediate].
-  auto swz = [](int s) -> int { return (LPR == 8 ? (s >> 1) : s * (8 / LPR)) & (UPW - 1); };
-  auto slot = [&](int s, int g) -> int { return s * UPW + (g ^ swz(s)); };
-  constexpr int kSwzStep = LPR == 8 ? 1 : 8 / LPR;      // swz(s) in {0,1,2,3} * kSwzStep
+  static_assert(SPL % PT == 0 || PT % SPL == 0, "a lane's samples must not straddle levels unevenly");
+  // Record slot of (sample s, lane group g): s*UPW + (g ^ swz(s)), swz(s) = (s / SPL) * (8 / LPR): the phase-1
+  // STS.128 of a quarter-warp (8 lanes = 8/LPR groups x LPR sample owners) then hits 8 different 16-byte bank
+  // groups (needs UPW >= 8; with UPW = 4 the store is 2-way conflicted).  swz(s) takes LPR values.
+  auto swz = [](int s) -> int { return ((s / SPL) * (8 / LPR)) & (UPW - 1); };
 
   __shared__ int sH[NL], sW[NL], sStart[NL], sTileCum[NL + 1];
   __shared__ float sHf[NL], sWf[NL];
-  extern __shared__ float4 sRecAll[];   // [NW][LPT][UPW]
+  extern __shared__ float4 sRecAll[];   // [NW][2][LPT][UPW]
 
   const int M = p.M, Lq = p.Lq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -240,29 +225,46 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
   }
   __syncthreads();
 
-  const int cstride = CSB ? CSB : M * D * EB;      // bytes between horizontally adjacent pixels
-  int rstride[NL];                                  // bytes between vertically adjacent pixels, per level
-#pragma unroll
-  for (int l = 0; l < NL; ++l) rstride[l] = sW[l] * cstride;
-
+  const int cstride = M * D * EB;                   // bytes between horizontally adjacent pixels
   const int tiles_per_bm = pyramid ? sTileCum[NL] : (Lq + p.tile_q - 1) / p.tile_q;
   const long long total_tiles = (long long)p.N * tiles_per_bm * M;
   const int chunks_per_warp = (p.tile_q + NW * UPW - 1) / (NW * UPW);   // warp steps per tile
-  float4* sRec = sRecAll + (size_t)warp * LPT * UPW;
-  const float4* sRecG[4];                           // this lane group's record column under each swizzle value
+  // REC16: one record {offset | corner mask, lh, lw, attn}, weights rebuilt in phase 2 (half the record wavefronts on
+  // the L1 data pipe, ~18 more instructions per sample step); else two: {offset, dy, attn, dx | mask} {w1, w2, w3, w4}
+  constexpr int RECS = REC16 ? 1 : 2;
+  float4* sRecA = sRecAll + (size_t)warp * RECS * LPT * UPW;
+  float4* sRecB = sRecA + (REC16 ? 0 : LPT * UPW);
+  int rstride[NL];                                  // bytes between vertically adjacent pixels, per level
 #pragma unroll
-  for (int c = 0; c < 4; ++c) sRecG[c] = sRec + (g ^ ((c * kSwzStep) & (UPW - 1)));
+  for (int l = 0; l < NL; ++l) rstride[l] = sW[l] * cstride;
   const float inv_p = 1.0f / (float)PT;
+  const int lvl0 = (k * SPL) / PT;                  // first level of this lane's samples
 
   // ---- work cursor: (tile, chunk) pairs of this warp, flattened so the next step can be prefetched ----
-  long long tile = blockIdx.x;
+  // walk 0 (default): tile = blockIdx.x + i * gridDim.x with heads varying fastest: all CTAs work on the same frame
+  //   (its value map stays in L2) and the 8 heads of a query block stream the same loc/attn DRAM pages together.
+  // walk 1 (diagnostic): a CTA owns a CONTIGUOUS range of tiles, spatial index fastest inside one (batch, head),
+  //   pyramid rows boustrophedon.  Measured: no L1 gain (a tile's own working set already exceeds L1, hit rate
+  //   81.2 % either way) and 1.65x the DRAM reads at 8 frames (8 value maps in flight > L2): profiles/r01_walk_ncu.txt.
+  const bool raster = p.walk == 1;
+  const long long tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  long long tile = raster ? (long long)blockIdx.x * tiles_per_cta : (long long)blockIdx.x;
+  const long long tile_end = raster ? (tile + tiles_per_cta < total_tiles ? tile + tiles_per_cta : total_tiles) : total_tiles;
+  const long long tile_step = raster ? 1 : (long long)gridDim.x;
   int chunk = 0;
   int t_m = 0, t_b = 0, t_t = 0, t_lvl = 0, t_ty = 0, t_tx = 0;
   auto decode_tile = [&]() {
-    t_m = (int)(tile % M);
-    const long long r = tile / M;
-    t_t = (int)(r % tiles_per_bm);
-    t_b = (int)(r / tiles_per_bm);
+    if (raster) {
+      t_t = (int)(tile % tiles_per_bm);
+      const long long r = tile / tiles_per_bm;
+      t_m = (int)(r % M);
+      t_b = (int)(r / M);
+    } else {
+      t_m = (int)(tile % M);
+      const long long r = tile / M;
+      t_t = (int)(r % tiles_per_bm);
+      t_b = (int)(r / tiles_per_bm);
+    }
     if (pyramid) {
       t_lvl = 0;
       while (t_lvl + 1 < NL && t_t >= sTileCum[t_lvl + 1]) ++t_lvl;
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
       const int ntx = (sW[t_lvl] + (1 << tw_log2) - 1) >> tw_log2;
       t_ty = tt / ntx;
       t_tx = tt - t_ty * ntx;
+      if (raster && (t_ty & 1)) t_tx = ntx - 1 - t_tx;
     }
   };
   auto locate = [&](bool& valid, size_t& bq, size_t& unit) {
@@ -286,37 +289,32 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
     bq = (size_t)t_b * Lq + (valid ? qi : 0);
     unit = bq * M + t_m;
   };
-  auto prefetch = [&](Prefetched<SPL, FUSED>& pf, size_t bq, size_t unit) {
+  auto prefetch = [&](Prefetched<SPL, NLV, FUSED>& pf, size_t bq, size_t unit) {
     if constexpr (FUSED) {
+      // rows of offsets / logits may be slices of one merged projection output (pitch > dense row length)
+      ld_stream_vec<SPL>(p.logits + bq * p.logit_pitch + t_m * LPT + k * SPL, pf.lg);
+      ld_stream_vec<2 * SPL>(p.offsets + bq * p.off_pitch + (t_m * LPT + k * SPL) * 2, pf.off);
 #pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        const int s = i * LPR + k;
-        // rows of offsets / logits may be slices of one merged projection output (pitch > dense row length)
-        pf.lg[i] = ld_stream_f1(p.logits + bq * p.logit_pitch + t_m * LPT + s);
-        pf.off[i] = ld_stream_f2(p.offsets + bq * p.off_pitch + (t_m * LPT + s) * 2);
-        const float* rp = p.ref + (bq * NL + s / PT) * p.ref_dim;
+      for (int j = 0; j < NLV; ++j) {
+        const float* rp = p.ref + (bq * NL + lvl0 + j) * p.ref_dim;
         if (p.ref_dim == 4) {
-          pf.ref[i] = __ldg(reinterpret_cast<const float4*>(rp));
+          pf.ref[j] = __ldg(reinterpret_cast<const float4*>(rp));
         } else {
           const float2 r2 = __ldg(reinterpret_cast<const float2*>(rp));
-          pf.ref[i] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
+          pf.ref[j] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
         }
       }
     } else {
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        const int s = i * LPR + k;
-        pf.xy[i] = ld_stream_f2(p.loc + (unit * LPT + s) * 2);
-        pf.a[i] = ld_stream_f1(p.attn + unit * LPT + s);
-      }
+      ld_stream_vec<2 * SPL>(p.loc + (unit * LPT + k * SPL) * 2, pf.xy);
+      ld_stream_vec<SPL>(p.attn + unit * LPT + k * SPL, pf.a);
     }
   };
 
-  bool have = tile < total_tiles;
+  bool have = tile < tile_end;
   bool n_valid = false;
   size_t n_bq = 0, n_unit = 0;
   const char* n_vbase = nullptr;
-  Prefetched<SPL, FUSED> pf;
+  Prefetched<SPL, NLV, FUSED> pf;
   if (have) {
     decode_tile();
     locate(n_valid, n_bq, n_unit);
@@ -333,51 +331,81 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
     {
       float a[SPL], lx[SPL], ly[SPL];
       if constexpr (FUSED) {
-        // softmax over the unit's LPT logits in the operation order of PyTorch's persistent warp softmax
-        // (element e on virtual lane e % WS, per-lane sequential sum, xor butterfly WS/2..1)
-        constexpr int NP2 = fast_next_pow2(LPT), WS = NP2 < 32 ? NP2 : 32, R = WS / LPR;
-        float mx = -INFINITY;
+        // softmax over the unit's LPT logits in the operation order of PyTorch's persistent warp softmax for
+        // <= 32 elements: one element per virtual lane, xor butterfly over the element index WS/2 .. 1.  Element
+        // e = k*SPL + i lives in register i of lane k: index bits >= log2(SPL) are lane bits (shuffle), the rest
+        // are register bits (in-lane pairs).  fp32 addition is commutative, so both partners get the same sum.
+        constexpr int WS = fast_next_pow2(LPT);
+        static_assert(WS == LPT && WS <= 32, "fused fast path: L*P must be a power of two <= 32");
+        float mx = pf.lg[0];
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) mx = fmaxf(mx, pf.lg[i]);
+        for (int i = 1; i < SPL; ++i) mx = fmaxf(mx, pf.lg[i]);
 #pragma unroll
         for (int off = LPR / 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        float vs[R];
+        float v[SPL];
 #pragma unroll
-        for (int j = 0; j < R; ++j) vs[j] = 0.0f;
+        for (int i = 0; i < SPL; ++i) { a[i] = expf(__fsub_rn(pf.lg[i], mx)); v[i] = a[i]; }
+#pragma unroll
+        for (int o = WS / 2; o >= 1; o >>= 1) {
+          if (o >= SPL) {
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], o / SPL));
+          } else {
+            float t[SPL];
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) t[i] = __fadd_rn(v[i], v[i ^ o]);
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) v[i] = t[i];
+          }
+        }
+        const float sum = v[0];
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
-          a[i] = expf(__fsub_rn(pf.lg[i], mx));
-          vs[i % R] = __fadd_rn(vs[i % R], a[i]);
-        }
-#pragma unroll
-        for (int h = R / 2; h >= 1; h >>= 1) {
-#pragma unroll
-          for (int j = 0; j < h; ++j) vs[j] = __fadd_rn(vs[j], vs[j + h]);
-        }
-        float sum = vs[0];
-#pragma unroll
-        for (int off = LPR / 2; off >= 1; off >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, off));
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-          const int l = (i * LPR + k) / PT;
+          const int l = lvl0 + i / PT;
+          const float4 rf = pf.ref[i / PT];
           a[i] = __fdiv_rn(a[i], sum);
-          lx[i] = location_from_offset(pf.ref[i].x, pf.ref[i].z, pf.off[i].x, sWf[l], inv_p, p.ref_dim);
-          ly[i] = location_from_offset(pf.ref[i].y, pf.ref[i].w, pf.off[i].y, sHf[l], inv_p, p.ref_dim);
+          lx[i] = location_from_offset(rf.x, rf.z, pf.off[2 * i], sWf[l], inv_p, p.ref_dim);
+          ly[i] = location_from_offset(rf.y, rf.w, pf.off[2 * i + 1], sHf[l], inv_p, p.ref_dim);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) { lx[i] = pf.xy[i].x; ly[i] = pf.xy[i].y; a[i] = pf.a[i]; }
+        for (int i = 0; i < SPL; ++i) { lx[i] = pf.xy[2 * i]; ly[i] = pf.xy[2 * i + 1]; a[i] = pf.a[i]; }
       }
 #pragma unroll
       for (int i = 0; i < SPL; ++i) {
-        const int s = i * LPR + k;
-        const int l = s / PT;
-        const int Wl = sW[l];
-        const SampleGeom sg = sample_setup_f(lx[i], ly[i], sHf[l], sWf[l], sH[l], Wl);
-        const bool inr = valid && sg.in_range;
-        int packed = 0;
-        if (inr) packed = (((sStart[l] + sg.h_low * Wl + sg.w_low) * M * D) * EB) | sg.mask;
-        sRec[slot(s, g)] = make_float4(__int_as_float(packed), sg.lh, sg.lw, inr ? a[i] : 0.0f);
+        const int s = k * SPL + i;
+        const int l = lvl0 + i / PT;
+        const int Hl = sH[l], Wl = sW[l];
+        const float Hf = sHf[l], Wf = sWf[l];
+        // cuh:285-288 (one FFMA each), then cuh:39-45, :56-78 with the zero padding moved into the weights
+        const float h_im = __fmaf_rn(ly[i], Hf, -0.5f);
+        const float w_im = __fmaf_rn(lx[i], Wf, -0.5f);
+        const bool inr = valid && (h_im > -1.0f) && (w_im > -1.0f) && (h_im < Hf) && (w_im < Wf);
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h_low = inr ? (int)hf : 0, w_low = inr ? (int)wf : 0;
+        const float lh = __fsub_rn(h_im, hf), lw = __fsub_rn(w_im, wf);
+        const float hh = __fsub_rn(1.0f, lh), hw = __fsub_rn(1.0f, lw);
+        const bool top = inr && h_low >= 0, bot = inr && h_low + 1 <= Hl - 1;
+        const bool lef = inr && w_low >= 0, rig = inr && w_low + 1 <= Wl - 1;
+        const float fh0 = top ? hh : 0.0f, fh1 = bot ? lh : 0.0f;     // row factors (upper, lower)
+        const float fw0 = lef ? hw : 0.0f, fw1 = rig ? lw : 0.0f;     // column factors (left, right)
+        const int hb = top ? h_low : 0, wb = lef ? w_low : 0;         // h_low / w_low = -1 -> the valid neighbour 0
+        int off = ((sStart[l] + hb * Wl + wb) * M * D) * EB;
+        int dy = (top && bot) ? Wl * cstride : 0;
+        int dx = (lef && rig) ? cstride : 0;
+        // corner-live bits (cuh:56-78) ride in the low bits of dx (a multiple of 64): a corner that is outside the
+        // map, or belongs to a skipped sample (cuh:288), is not loaded at all -- every loaded byte costs L1 write-back
+        // bandwidth, the kernel's limiter -- its weight is 0 and its registers keep finite contents.
+        dx |= (int)(top && lef) | ((int)(top && rig) << 1) | ((int)(bot && lef) << 2) | ((int)(bot && rig) << 3);
+        const int sl = s * UPW + (g ^ swz(s));
+        if constexpr (REC16) {
+          const int cmask = dx & 15;
+          const int off0 = inr ? (((sStart[l] + h_low * Wl + w_low) * M * D) * EB) | cmask : 0;   // unclamped: masked corners are never dereferenced
+          sRecA[sl] = make_float4(__int_as_float(off0), lh, lw, inr ? a[i] : 0.0f);
+        } else {
+          sRecA[sl] = make_float4(__int_as_float(off), __int_as_float(dy), inr ? a[i] : 0.0f, __int_as_float(dx));
+          sRecB[sl] = make_float4(__fmul_rn(fh0, fw0), __fmul_rn(fh0, fw1), __fmul_rn(fh1, fw0), __fmul_rn(fh1, fw1));
+        }
       }
     }
     __syncwarp();
@@ -386,8 +414,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
     ++chunk;
     if (chunk == chunks_per_warp) {
       chunk = 0;
-      tile += gridDim.x;
-      have = tile < total_tiles;
+      tile += tile_step;
+      have = tile < tile_end;
       if (have) {
         decode_tile();
         n_vbase = reinterpret_cast<const char*>(p.value) +
@@ -399,65 +427,56 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
       prefetch(pf, n_bq, n_unit);
     }
 
-    // ---------------- phase 2: gather + weighted reduction ----------------
+    // ---------------- phase 2: gather + weighted reduction (branch-free) ----------------
     f32x2 acc[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) acc[j] = 0ull;
-    auto rec_at = [&](int s) -> float4 { return sRecG[(swz(s) / kSwzStep) & 3][s * UPW]; };
-    // warp-uniform three-way split per sample:
-    //   all 4 corners of all units valid -> plain loads, no zero-fill, no predicates                  (common)
-    //   every unit out of range          -> nothing issued, nothing accumulated (cuh:288)              (borders)
-    //   otherwise                        -> zero-filled, predicated loads = zero padding               (rare)
-    if constexpr (PD == 1) {
-#pragma unroll
-      for (int s = 0; s < LPT; ++s) {
-        const float4 rc = rec_at(s);
-        const int packed = __float_as_int(rc.x);
-        const int mk = packed & 15;
+    RowVec<VB> q[PD][4];
+    float4 wq[PD];
+    float at[PD];
+    auto issue = [&](int s, int d) {
+      const int sl = s * UPW + (g ^ swz(s));
+      const float4 ra = sRecA[sl];
+      if constexpr (REC16) {
+        const int packed = __float_as_int(ra.x);
+        const uint32_t m = (uint32_t)packed & 15u;
+        const float lh = ra.y, lw = ra.z;
+        const float hh = __fsub_rn(1.0f, lh), hw = __fsub_rn(1.0f, lw);
+        const float fh0 = (m & 3u) ? hh : 0.0f, fh1 = (m & 12u) ? lh : 0.0f;
+        const float fw0 = (m & 5u) ? hw : 0.0f, fw1 = (m & 10u) ? lw : 0.0f;
+        wq[d] = make_float4(__fmul_rn(fh0, fw0), __fmul_rn(fh0, fw1), __fmul_rn(fh1, fw0), __fmul_rn(fh1, fw1));
+        at[d] = ra.w;
         const char* c1 = vbase + (ptrdiff_t)(packed & ~15);
         const char* c3 = c1 + rstride[s / PT];
-        RowVec<VB> q1, q2, q3, q4;
-        if (__all_sync(0xffffffffu, mk == 15)) {
-          q1.load(c1);
-          q2.load(c1 + cstride);
-          q3.load(c3);
-          q4.load(c3 + cstride);
-          accumulate_sample<T, VB, NP>(acc, rc, q1, q2, q3, q4);
-        } else if (__any_sync(0xffffffffu, mk != 0)) {
-          q1.load_or_zero(c1, mk & 1);
-          q2.load_or_zero(c1 + cstride, mk & 2);
-          q3.load_or_zero(c3, mk & 4);
-          q4.load_or_zero(c3 + cstride, mk & 8);
-          accumulate_sample<T, VB, NP>(acc, rc, q1, q2, q3, q4);
-        }
+        q[d][0].load_if(c1, m & 1u);
+        q[d][1].load_if(c1 + cstride, m & 2u);
+        q[d][2].load_if(c3, m & 4u);
+        q[d][3].load_if(c3 + cstride, m & 8u);
+      } else {
+        wq[d] = sRecB[sl];
+        at[d] = ra.z;
+        const char* c1 = vbase + (uint32_t)__float_as_int(ra.x);
+        const char* c3 = c1 + (uint32_t)__float_as_int(ra.y);
+        const uint32_t dxm = (uint32_t)__float_as_int(ra.w), dx = dxm & ~15u;
+        q[d][0].load_if(c1, dxm & 1u);
+        q[d][1].load_if(c1 + dx, dxm & 2u);
+        q[d][2].load_if(c3, dxm & 4u);
+        q[d][3].load_if(c3 + dx, dxm & 8u);
       }
-    } else {
-      RowVec<VB> q[PD][4];
-      float4 rc[PD];
-      bool live[PD];            // warp-uniform: at least one unit takes this sample
-      auto issue = [&](int s, int d) {
-        rc[d] = rec_at(s);
-        const int packed = __float_as_int(rc[d].x);
-        const int mk = packed & 15;
-        const bool all_in = __all_sync(0xffffffffu, mk == 15);
-        live[d] = all_in || __any_sync(0xffffffffu, mk != 0);
-        if (live[d]) {
-          const char* c1 = vbase + (ptrdiff_t)(packed & ~15);
-          const char* c3 = c1 + rstride[s / PT];
-          q[d][0].load_sel(c1, mk & 1, all_in);          // zero-fill branched over inside the asm when all_in
-          q[d][1].load_sel(c1 + cstride, mk & 2, all_in);
-          q[d][2].load_sel(c3, mk & 4, all_in);
-          q[d][3].load_sel(c3 + cstride, mk & 8, all_in);
-        }
-      };
+    };
+    // registers of never-loaded corners must hold finite values (their weight is 0): clear them once per step, so
+    // a non-finite value can only reach outputs the reference also makes non-finite (same unit, same channels)
 #pragma unroll
-      for (int s = 0; s < PD - 1; ++s) issue(s, s);
+    for (int d = 0; d < PD; ++d)
 #pragma unroll
-      for (int s = 0; s < LPT; ++s) {
-        if (s + PD - 1 < LPT) issue(s + PD - 1, (s + PD - 1) % PD);
-        const int d = s % PD;
-        if (live[d]) accumulate_sample<T, VB, NP>(acc, rc[d], q[d][0], q[d][1], q[d][2], q[d][3]);
-      }
+      for (int c = 0; c < 4; ++c) q[d][c].zero();
+#pragma unroll
+    for (int s = 0; s < PD - 1; ++s) issue(s, s);
+#pragma unroll
+    for (int s = 0; s < LPT; ++s) {
+      if (s + PD - 1 < LPT) issue(s + PD - 1, (s + PD - 1) % PD);
+      const int d = s % PD;
+      accumulate_sample<T, VB, NP>(acc, wq[d], at[d], q[d][0], q[d][1], q[d][2], q[d][3]);
     }
     if (valid) {
       char* op = reinterpret_cast<char*>(p.out) + (unit * D + (size_t)k * VEC) * EB;
@@ -470,55 +489,61 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
 // -----------------------------------------------------------------------------------------------
 namespace {
 
-template <typename T, int D, int VB, int LPT, int PT, int CSB, bool FUSED, int NW, int MINB, int PD>
+template <typename T, int D, int VB, int LPT, int PT, bool FUSED, int NW, int MINB, int PD, bool REC16>
 int launch_fast(const FwdParams& p, cudaStream_t stream) {
   constexpr int LPR = D / (VB / (int)sizeof(T)), UPW = 32 / LPR;
-  const size_t smem = (size_t)NW * LPT * UPW * sizeof(float4);
-  auto kern = msda_fwd_fast_kernel<T, D, VB, LPT, PT, CSB, FUSED, NW, MINB, PD>;
+  const size_t smem = (size_t)NW * (REC16 ? 1 : 2) * LPT * UPW * sizeof(float4);
+  auto kern = msda_fwd_fast_kernel<T, D, VB, LPT, PT, FUSED, NW, MINB, PD, REC16>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    // the gather lives on L1 hits: shared memory only holds the records
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 20);
+    // the gather lives on L1 hits: shared memory only holds the records.  Ask for just enough carve-out that MINB
+    // CTAs fit (ncu: with too small a hint only ONE CTA was resident per SM).
+    const int need_kb = (int)((MINB * (smem + 1024 + 256) + 1023) / 1024);
+    int pct = (need_kb * 100 + 227) / 228 + 2;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
     configured = true;
   }
   kern<<<p.grid, NW * 32, smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
-template <typename T, int LPT, int PT, int CSB, bool FUSED>
+template <typename T, bool FUSED>
 int dispatch_fast_variant(const FwdParams& p, cudaStream_t stream) {
-  switch (p.variant) {   //                  D  VB                      NW MINB PD
+  constexpr int LPT = 16, PT = 4;
+  switch (p.variant) {   //                  D  VB                 NW MINB PD REC16
     default:
-    case 0: return launch_fast<T, 32, 16, LPT, PT, CSB, FUSED, 16, 2, 1>(p, stream);
-    case 1: return launch_fast<T, 32, 16, LPT, PT, CSB, FUSED, 8, 4, 1>(p, stream);
-    case 2: return launch_fast<T, 32, 32, LPT, PT, CSB, FUSED, 8, 2, 1>(p, stream);
-    case 3: return launch_fast<T, 32, 32, LPT, PT, CSB, FUSED, 8, 2, 2>(p, stream);
-    case 4: return launch_fast<T, 32, 32, LPT, PT, CSB, FUSED, 16, 1, 2>(p, stream);
-    case 5: return launch_fast<T, 32, 32, LPT, PT, CSB, FUSED, 4, 4, 2>(p, stream);
-    case 6: return launch_fast<T, 32, 32, LPT, PT, CSB, FUSED, 16, 1, 1>(p, stream);
-    case 7: return launch_fast<T, 32, 16, LPT, PT, CSB, FUSED, 8, 3, 2>(p, stream);
-    case 8: return launch_fast<T, 32, 16, LPT, PT, CSB, FUSED, 4, 8, 1>(p, stream);
-    case 9: return launch_fast<T, 32, 32, LPT, PT, CSB, FUSED, 8, 3, 1>(p, stream);
+    case 0: return launch_fast<T, 32, 32, LPT, PT, FUSED, 8, 2, 1, false>(p, stream);
+    case 1: return launch_fast<T, 32, 32, LPT, PT, FUSED, 8, 2, 1, true>(p, stream);
+    case 2: return launch_fast<T, 32, 32, LPT, PT, FUSED, 8, 3, 1, true>(p, stream);
+    case 3: return launch_fast<T, 32, 16, LPT, PT, FUSED, 8, 4, 1, true>(p, stream);
+    case 4: return launch_fast<T, 32, 16, LPT, PT, FUSED, 8, 3, 2, true>(p, stream);
+    case 5: return launch_fast<T, 32, 16, LPT, PT, FUSED, 8, 3, 2, false>(p, stream);
+    case 6: return launch_fast<T, 32, 16, LPT, PT, FUSED, 16, 2, 1, true>(p, stream);
+    case 7: return launch_fast<T, 32, 32, LPT, PT, FUSED, 8, 2, 2, true>(p, stream);
   }
 }
 
 template <typename T>
 int dispatch_fast(const FwdParams& p, cudaStream_t stream) {
-  const bool fused = p.loc == nullptr;
-  constexpr int EB = (int)sizeof(T);
-  const bool csb = (p.M * p.D == 256);   // M*D = 256: the pixel pitch becomes an immediate
-  if (fused) {
-    return csb ? dispatch_fast_variant<T, 16, 4, 256 * EB, true>(p, stream)
-               : dispatch_fast_variant<T, 16, 4, 0, true>(p, stream);
-  }
-  return csb ? dispatch_fast_variant<T, 16, 4, 256 * EB, false>(p, stream)
-             : dispatch_fast_variant<T, 16, 4, 0, false>(p, stream);
+  return p.loc == nullptr ? dispatch_fast_variant<T, true>(p, stream) : dispatch_fast_variant<T, false>(p, stream);
 }
+
+inline bool aligned_to(const void* ptr, uintptr_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) == 0; }
 
 }  // namespace
 
-bool fast_supported(int D, int L, int P) { return D == 32 && L == 4 && P == 4; }
+int fast_variant_count() { return 8; }
+
+// The fast kernels read a lane's phase-1 operands with one vector load: the operand rows must be 32-byte aligned.
+bool fast_supported(const FwdParams& p) {
+  if (!(p.D == 32 && p.L == 4 && p.P == 4)) return false;
+  if (!aligned_to(p.value, 32) || !aligned_to(p.out, 32)) return false;
+  if (p.loc) return aligned_to(p.loc, 32) && aligned_to(p.attn, 32);
+  return aligned_to(p.offsets, 32) && aligned_to(p.logits, 32) && (p.off_pitch % 8) == 0 && (p.logit_pitch % 8) == 0 &&
+         aligned_to(p.ref, p.ref_dim == 4 ? 16 : 8);
+}
+bool fast_shape_supported(int D, int L, int P) { return D == 32 && L == 4 && P == 4; }
 int launch_forward_fast_f32(const FwdParams& p, cudaStream_t stream) { return dispatch_fast<float>(p, stream); }
 int launch_forward_fast_bf16(const FwdParams& p, cudaStream_t stream) { return dispatch_fast<__nv_bfloat16>(p, stream); }
 

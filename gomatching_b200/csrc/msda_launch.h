@@ -29,6 +29,7 @@ struct FwdParams {
   int grid;                   // CTAs to launch
   int variant;                // kernel instantiation
   int force_v1;               // use the runtime-L*P tiled kernel even where the specialised one applies
+  int walk;                   // fast kernels: 0 strided heads-fastest tile walk, 1 contiguous raster walk per CTA (diagnostic)
 };
 
 // Each returns a cudaError_t cast to int (0 = ok) or MSDA_E_UNSUPPORTED (-5).
@@ -39,7 +40,9 @@ int launch_forward_f64(const double* value, const int64_t* shapes, const int64_t
                        cudaStream_t stream);
 int forward_variant_count();
 // compile-time-specialised kernels for the DeepSolo configuration (msda_forward_fast.cu)
-bool fast_supported(int D, int L, int P);
+bool fast_shape_supported(int D, int L, int P);
+bool fast_supported(const FwdParams& p);   // shape + the 32-byte operand alignment the vector loads need
+int fast_variant_count();
 int launch_forward_fast_f32(const FwdParams& p, cudaStream_t stream);
 int launch_forward_fast_bf16(const FwdParams& p, cudaStream_t stream);
 // true if the tiled kernels can run this problem (else only the generic kernel can)

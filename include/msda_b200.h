@@ -65,7 +65,7 @@ typedef struct msda_b200_tuning {
   int32_t tile_q;        /* linear tile length in queries (0 = default)                            */
   int32_t ctas_per_sm;   /* persistent grid = SM count * ctas_per_sm (0 = default)                 */
   int32_t variant;       /* kernel instantiation selector, see msda_b200_variant_count (0 = default)*/
-  int32_t reserved[2];
+  int32_t reserved[2];   /* [0] = 1: force the runtime-L*P tiled kernel; [1] = 1: contiguous raster tile walk (diagnostics) */
 } msda_b200_tuning_t;
 
 int         msda_b200_abi_version(void);

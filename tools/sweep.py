@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--force-v1", type=int, default=0)
+    ap.add_argument("--walk", type=int, default=0)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -68,14 +69,15 @@ def main():
 
     results = []
     variants = range(_native.lib().msda_b200_variant_count())
-    cps_list = [1, 2, 3, 4, 6, 8] if not args.quick else [2, 4]
+    cps_list = [1, 2, 3, 4, 6, 8] if not args.quick else [2, 3, 4]
     tiles = []
     if args.kind == "encoder":
         tiles += [dict(mode=2, tile_h=h, tile_w=w) for h, w in
-                  [(4, 8), (4, 16), (8, 8), (8, 16), (16, 8), (16, 16), (8, 32), (16, 32), (4, 32), (2, 32), (32, 32)]]
-    tiles += [dict(mode=1, tile_q=q) for q in (16, 32, 64, 128, 256)]
+                  ([(8, 16), (16, 8), (16, 16), (8, 32), (16, 32)] if args.quick else
+                   [(4, 8), (4, 16), (8, 8), (8, 16), (16, 8), (16, 16), (8, 32), (16, 32), (4, 32), (2, 32), (32, 32)])]
+    tiles += [dict(mode=1, tile_q=q) for q in ((64, 128, 256) if args.quick else (16, 32, 64, 128, 256))]
     for v, t, cps in itertools.product(variants, tiles, cps_list):
-        tn = dict(t, variant=v, ctas_per_sm=cps, force_v1=args.force_v1)
+        tn = dict(t, variant=v, ctas_per_sm=cps, force_v1=args.force_v1, walk=args.walk)
         try:
             us = time_launches(runner(tn), sets, args.iters)
         except Exception as e:  # noqa: BLE001
@@ -90,6 +92,10 @@ def main():
     for r in results[:12]:
         print("%8.2f us %7.0f GB/s  %s" % (r["us"], r["gbs"], r["tuning"]))
     print("worst: %.2f us %s" % (results[-1]["us"], results[-1]["tuning"]))
+    for v in variants:
+        best = next((r for r in results if r["tuning"]["variant"] == v), None)
+        if best:
+            print("best of variant %d: %8.2f us %7.0f GB/s  %s" % (v, best["us"], best["gbs"], best["tuning"]))
     generic = time_launches(runner(dict(mode=3)), sets, 6) if not args.fused else None
     if generic:
         print("generic kernel: %.2f us" % generic)
