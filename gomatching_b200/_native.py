@@ -24,6 +24,9 @@ SYMBOLS = (
     "msda_b200_forward_bf16_ex",
     "msda_b200_forward_fused_f32",
     "msda_b200_forward_fused_bf16",
+    "msda_b200_linear_split_weight_f32",
+    "msda_b200_linear_f32",
+    "msda_b200_linear_set_trace",
     "msda_b200_forward_fused_pitched_f32",
     "msda_b200_forward_fused_pitched_bf16",
     "msda_b200_locations_softmax_f32",
@@ -102,6 +105,12 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_host_ctx_destroy.argtypes = [vp]
         L.msda_b200_forward_f32_host.restype = ci
         L.msda_b200_forward_f32_host.argtypes = [vp] * 6 + [ci] * 7 + [vp]
+        L.msda_b200_linear_split_weight_f32.restype = ci
+        L.msda_b200_linear_split_weight_f32.argtypes = [vp, ci, ci, vp, vp, vp]
+        L.msda_b200_linear_f32.restype = ci
+        L.msda_b200_linear_f32.argtypes = [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp]
+        L.msda_b200_linear_set_trace.restype = None
+        L.msda_b200_linear_set_trace.argtypes = [vp]
         if L.msda_b200_abi_version() != 1:
             raise MSDAError("libmsda_b200.so ABI version mismatch")
         _lib = L

@@ -3,8 +3,10 @@
 Same constructor, same parameter names and shapes (``sampling_offsets``, ``attention_weights``,
 ``value_proj``, ``output_proj`` -- DeepSolo / Deformable-DETR checkpoints load unchanged), same
 initialisation (:99-115), same ``forward`` signature and errors.  The core runs on the hand-written
-sm_100a kernels through the C ABI; the four dense projections stay ``nn.Linear`` (cuBLAS tensor-core
-GEMMs -- they border the op, they are not it).
+sm_100a kernels through the C ABI.  The four dense projections bordering it are ``nn.Linear`` parameters; at
+inference on fp32 CUDA tensors they run on the tcgen05 tensor cores as 3xTF32 GEMMs with fp32-grade accuracy
+(``projections.linear_3xtf32``, csrc/proj_gemm.cu; ``tensor_core_projections = False`` restores ``F.linear``), with the
+padding-mask ``masked_fill`` of ms_deform_attn.py:135 fused into the value_proj epilogue.
 
 Inference (no autograd): softmax, offset->location and sampling run as ONE fused kernel, so
 ``sampling_locations`` / ``attention_weights`` are never written to HBM.  With autograd the reference's
@@ -21,6 +23,7 @@ from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
 from .ms_deform_attn_func import (MSDeformAttnFunction, fused_supported, ms_deform_attn_forward_fused)
+from .projections import linear_3xtf32
 
 
 def _is_power_of_2(n):
@@ -49,6 +52,7 @@ class MSDeformAttn(nn.Module):
         self.n_points = n_points
         self.use_fused = True      # fused glue+sampler kernel when no gradient is needed
         self.merge_query_projections = True   # inference: sampling_offsets || attention_weights as ONE 256->384 GEMM
+        self.tensor_core_projections = True   # inference, fp32 CUDA: projections as 3xTF32 tcgen05 GEMMs (fp32-grade)
         self._qproj_cache = None
         self.tuning = None         # optional msda_b200_tuning_t fields (dict); never changes results
 
@@ -109,23 +113,37 @@ class MSDeformAttn(nn.Module):
         M, L, P = self.n_heads, self.n_levels, self.n_points
         D = self.d_model // M
 
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
-        value = value.view(N, Len_in, M, D)
         needs_grad = torch.is_grad_enabled() and (
             query.requires_grad or input_flatten.requires_grad or reference_points.requires_grad
             or any(p.requires_grad for p in self.parameters()))
+        C = self.d_model
+        tc = (self.tensor_core_projections and not needs_grad and query.is_cuda and input_flatten.is_cuda
+              and query.dtype == torch.float32 and input_flatten.dtype == torch.float32
+              and self.value_proj.weight.dtype == torch.float32 and C % 32 == 0 and (M * L * P) % 32 == 0)
+
+        if tc:
+            value = linear_3xtf32(input_flatten, self.value_proj.weight, self.value_proj.bias,
+                                  row_zero=input_padding_mask)         # :133 + :135 in one kernel
+        else:
+            value = self.value_proj(input_flatten)
+            if input_padding_mask is not None:
+                value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, Len_in, M, D)
         fused_ok = (self.use_fused and not needs_grad and value.is_cuda
                     and value.dtype in (torch.float32, torch.bfloat16) and fused_supported(value.dtype, D, L, P))
         if fused_ok and self.merge_query_projections:
             # both projections read the same `query` (ms_deform_attn.py:137-138): one GEMM, and the fused kernel
             # takes the two column slices of its output as row-pitched views -- no copy, no second pass over query
             w, b = self._merged_query_projection()
-            qp = F.linear(query, w, b)
+            qp = linear_3xtf32(query, w, b) if tc else F.linear(query, w, b)
             n_off = M * L * P * 2
             sampling_offsets = qp[..., :n_off].view(N, Len_q, M, L, P, 2)
             attention_weights = qp[..., n_off:].view(N, Len_q, M, L * P)
+        elif tc:
+            sampling_offsets = linear_3xtf32(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(
+                N, Len_q, M, L, P, 2)
+            attention_weights = linear_3xtf32(query, self.attention_weights.weight, self.attention_weights.bias).view(
+                N, Len_q, M, L * P)
         else:
             sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
             attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
@@ -147,4 +165,6 @@ class MSDeformAttn(nn.Module):
             output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                                 sampling_locations.contiguous(), attention_weights.contiguous(),
                                                 self.im2col_step)
+        if tc and output.dtype == torch.float32:
+            return linear_3xtf32(output, self.output_proj.weight, self.output_proj.bias)     # :153
         return self.output_proj(output)

@@ -1,0 +1,76 @@
+"""Tensor-core projections bordering the sampler: nn.Linear replaced by the 3xTF32 tcgen05 GEMM of csrc/proj_gemm.cu.
+
+Reference being replaced: the four ``nn.Linear`` calls of ``MSDeformAttn.forward``
+(third_party/adet/layers/ms_deform_attn.py:133 value_proj (+ :135 masked_fill), :137 sampling_offsets,
+:138 attention_weights, :153 output_proj), fp32 cuBLAS GEMMs in the reference.
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+
+from . import _native
+
+_split_cache: "dict[int, tuple]" = {}
+
+
+def split_weight(weight: torch.Tensor):
+    """(w_hi, w_lo) TF32 head / remainder of an (N, K) fp32 weight, cached until the weight is modified or freed."""
+    key = id(weight)
+    hit = _split_cache.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3], hit[4]
+    if not weight.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    w = weight.detach()
+    if w.dtype != torch.float32:
+        raise TypeError("linear_3xtf32: fp32 weights only")
+    w = w.contiguous()
+    N, K = w.shape
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _native.check(_native.lib().msda_b200_linear_split_weight_f32(
+        w.data_ptr(), N, K, hi.data_ptr(), lo.data_ptr(), torch.cuda.current_stream(w.device).cuda_stream),
+        "msda_b200_linear_split_weight_f32")
+    ref = weakref.ref(weight, lambda _r, k=key: _split_cache.pop(k, None))
+    _split_cache[key] = (ref, weight._version, weight.data_ptr(), hi, lo)
+    return hi, lo
+
+
+def linear_3xtf32(x: torch.Tensor, weight: torch.Tensor, bias: "torch.Tensor | None" = None,
+                  row_zero: "torch.Tensor | None" = None, out: "torch.Tensor | None" = None) -> torch.Tensor:
+    """``F.linear(x, weight, bias)`` for fp32 CUDA tensors on the tcgen05 tensor cores with fp32-grade accuracy.
+
+    x (..., K) with a contiguous last dim (row pitch may exceed K); weight (N, K); returns (..., N).
+    row_zero: optional bool/uint8 tensor with one entry per row of x: rows flagged non-zero come out as zeros.
+    """
+    if not x.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    if x.dtype != torch.float32:
+        raise TypeError("linear_3xtf32: fp32 activations only")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    hi, lo = split_weight(weight)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+    y2 = out.view(-1, N) if out.is_contiguous() else out
+    if y2.dim() != 2 or y2.shape[0] != M or y2.stride(1) != 1:
+        raise ValueError("linear_3xtf32: out must be (M, N) with unit column stride")
+    rz = None
+    if row_zero is not None:
+        rz = row_zero.reshape(-1)
+        if rz.dtype == torch.bool:
+            rz = rz.view(torch.uint8)
+        rz = rz.contiguous()
+        if rz.numel() != M:
+            raise ValueError("row_zero must have one entry per row of x")
+    b = bias.detach().contiguous() if bias is not None else None
+    _native.check(_native.lib().msda_b200_linear_f32(
+        x2.data_ptr(), x2.stride(0), hi.data_ptr(), lo.data_ptr(), b.data_ptr() if b is not None else None,
+        rz.data_ptr() if rz is not None else None, M, N, K, y2.data_ptr(), y2.stride(0),
+        torch.cuda.current_stream(x.device).cuda_stream), "msda_b200_linear_f32")
+    return out

@@ -164,6 +164,22 @@ int msda_b200_backward_f32(const float* value, const int64_t* shapes, const int6
                            int N, int S, int M, int D, int L, int Lq, int P,
                            float* grad_value, float* grad_loc, float* grad_attn, void* stream);
 
+/* ---- bordering projections on the tensor cores (tcgen05 / TMEM / TMA, 3xTF32 = fp32-grade accuracy) ----------
+ * Replace the four nn.Linear calls of MSDeformAttn.forward (ms_deform_attn.py:133 value_proj, :137 sampling_offsets,
+ * :138 attention_weights, :153 output_proj), which the reference runs as fp32 cuBLAS GEMMs:
+ *     y[M, N] (row pitch ldy floats) = x[M, K] (row pitch ldx floats) . w[N, K]^T + bias[N]
+ * w is given pre-split into its TF32 head and remainder (msda_b200_linear_split_weight_f32, once per weight).
+ * row_zero (M bytes, may be NULL): rows with a non-zero byte are written as zeros -- the padding-mask
+ * masked_fill of ms_deform_attn.py:135 fused into the value_proj epilogue.
+ * K % 16 == 0, N % 32 == 0, N <= 1024, ldx % 4 == 0, ldy % 4 == 0, 16-byte aligned pointers. */
+int msda_b200_linear_split_weight_f32(const float* w, int N, int K, float* w_hi, float* w_lo, void* stream);
+int msda_b200_linear_f32(const float* x, int ldx, const float* w_hi, const float* w_lo, const float* bias,
+                         const unsigned char* row_zero, int M, int N, int K, float* y, int ldy, void* stream);
+/* diagnostics: per-CTA clock64 stamps of the following msda_b200_linear_f32 launches are written to buf
+ * (device memory, [CTAs][8] int64: start, first stage full, split done, last MMA issued, accumulator ready,
+ * epilogue done); NULL switches tracing off.  tools/gemm_trace.py. */
+void msda_b200_linear_set_trace(long long* buf);
+
 /* ---- host-buffer entry: what a non-PyTorch host (the cgo/JNI/ctypes stub of INTEGRATION.md) calls --
  * All tensor pointers are HOST pointers (pinned for full PCIe speed, pageable works).  Copies the
  * inputs to a device workspace owned by the handle, runs the core forward, copies the result back,

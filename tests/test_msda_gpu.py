@@ -273,7 +273,8 @@ def test_fused_equals_unfused(kind, dtype):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", MODULE)
 @pytest.mark.parametrize("fused", [True, False])
-def test_module_matches_reference_module_output(module_cases, name, fused):
+@pytest.mark.parametrize("tc", [True, False])
+def test_module_matches_reference_module_output(module_cases, name, fused, tc):
     import gomatching_b200 as g
     c = module_cases.case(name)
     d_model, levels, heads, points = (int(v) for v in c["cfg"])
@@ -281,6 +282,7 @@ def test_module_matches_reference_module_output(module_cases, name, fused):
     mod.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("sd/")}, strict=True)
     mod = mod.cuda().eval()
     mod.use_fused = fused
+    mod.tensor_core_projections = tc      # 3xTF32 tcgen05 projections vs F.linear (cuBLAS fp32)
     mask = dev(c["mask"]) if c["mask"].size else None
     torch.backends.cuda.matmul.allow_tf32 = False
     with torch.no_grad():
@@ -498,3 +500,24 @@ def test_module_merged_projection_matches_separate_projections(module_cases):
     assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
     assert rel_err(c2.cpu().numpy(), d2.cpu().numpy()) <= 1e-5
     assert rel_err(a.cpu().numpy(), c2.cpu().numpy()) > 1e-4
+
+
+def test_module_tensor_core_projections_match_cublas_fp32(module_cases):
+    """Same module, projections on the tcgen05 tensor cores (3xTF32) vs cuBLAS fp32: outputs agree to fp32 rounding,
+    far inside the 1e-4 bar -- so the projections cannot move a sampling index by more than a cuBLAS re-ordering would."""
+    import gomatching_b200 as g
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for name in ("ref2_mask", MODULE[0]):
+        c = module_cases.case(name)
+        d_model, levels, heads, points = (int(v) for v in c["cfg"])
+        mod = g.MSDeformAttn(d_model, levels, heads, points)
+        mod.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("sd/")}, strict=True)
+        mod = mod.cuda().eval()
+        mask = dev(c["mask"]) if c["mask"].size else None
+        args = (dev(c["query"]), dev(c["ref"]), dev(c["src"]), dev(c["shapes"]), dev(c["lsi"]), mask)
+        with torch.no_grad():
+            mod.tensor_core_projections = True
+            a = mod(*args)
+            mod.tensor_core_projections = False
+            b = mod(*args)
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
