@@ -452,6 +452,17 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
     return (int)cudaGetLastError();
   }
   const int LP = p.L * p.P;
+  if (p.mode == kModeStaged) {
+    if (sizeof(T) != 4 || !staged_supported(p)) return MSDA_E_UNSUPPORTED;
+    int rc = launch_forward_staged_f32(p, stream);      // queries of pyramid levels 0 .. staged_levels-1
+    if (rc || p.staged_levels >= p.L) return rc;
+    FwdParams rest = p;                                  // the coarser query levels: register-gather kernel
+    rest.mode = kModeLinear;
+    rest.q_level_begin = p.staged_levels;
+    rest.grid = p.grid * 4;
+    rest.variant = 3;
+    return launch_forward_fast_f32(rest, stream);
+  }
   if (fast_supported(p) && !p.force_v1)
     return sizeof(T) == 4 ? launch_forward_fast_f32(p, stream) : launch_forward_fast_bf16(p, stream);
   if (p.D == 32) {

@@ -26,153 +26,11 @@
 //     reference's skipped corner: identical unless v is Inf/NaN at a clamped border pixel.)
 //   * the next step's loc/attn (or offsets/logits/reference points) are prefetched into registers before the
 //     current step's gather starts, so their DRAM latency hides behind the gather.
-#include "msda_device.cuh"
+#include "msda_fast_common.cuh"
 #include "msda_launch.h"
 #include "../../include/msda_b200.h"
 
 namespace msda {
-
-__host__ __device__ constexpr int fast_next_pow2(int x) { int r = 1; while (r < x) r <<= 1; return r; }
-
-// ---- packed fp32x2 arithmetic (one instruction, two IEEE-rounded results) ------------------------------
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// ---- a VB-byte slice of a value row held in registers ------------------------------------------------
-template <int VB> struct RowVec;
-template <> struct RowVec<16> {
-  uint4 a;
-  __device__ __forceinline__ void load(const void* p) {
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
-  }
-  // loads only if pred != 0; otherwise the registers keep their (finite) contents and nothing is written back
-  __device__ __forceinline__ void load_if(const void* p, uint32_t pred) {
-    asm volatile("{\n .reg .pred pq;\n setp.ne.u32 pq, %5, 0;\n @pq ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
-                 : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w) : "l"(p), "r"(pred));
-  }
-  __device__ __forceinline__ void zero() { a = make_uint4(0, 0, 0, 0); }
-  __device__ __forceinline__ uint32_t word(int i) const { return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w; }
-};
-template <> struct RowVec<32> {
-  uint4 lo, hi;
-  __device__ __forceinline__ void load(const void* p) {
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
-                 : "l"(p));
-  }
-  __device__ __forceinline__ void load_if(const void* p, uint32_t pred) {
-    asm volatile("{\n .reg .pred pq;\n setp.ne.u32 pq, %9, 0;\n @pq ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n}"
-                 : "+r"(lo.x), "+r"(lo.y), "+r"(lo.z), "+r"(lo.w), "+r"(hi.x), "+r"(hi.y), "+r"(hi.z), "+r"(hi.w)
-                 : "l"(p), "r"(pred));
-  }
-  __device__ __forceinline__ void zero() { lo = make_uint4(0, 0, 0, 0); hi = lo; }
-  __device__ __forceinline__ uint32_t word(int i) const {
-    return i == 0 ? lo.x : i == 1 ? lo.y : i == 2 ? lo.z : i == 3 ? lo.w : i == 4 ? hi.x : i == 5 ? hi.y : i == 6 ? hi.z : hi.w;
-  }
-};
-
-// channel pair j (channels 2j, 2j+1) of a row slice as packed fp32x2
-template <typename T, int VB>
-__device__ __forceinline__ f32x2 chan_pair(const RowVec<VB>& r, int j) {
-  if constexpr (sizeof(T) == 4) {
-    return pk(__uint_as_float(r.word(2 * j)), __uint_as_float(r.word(2 * j + 1)));
-  } else {   // one 32-bit word holds two bf16: low half = even channel
-    const uint32_t w = r.word(j);
-    return pk(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-  }
-}
-
-template <typename T, int NP>
-__device__ __forceinline__ void store_row(void* p, const f32x2 (&acc)[NP]) {
-  float f[2 * NP];
-#pragma unroll
-  for (int j = 0; j < NP; ++j) upk(acc[j], f[2 * j], f[2 * j + 1]);
-  if constexpr (sizeof(T) == 4) {
-    if constexpr (NP == 2) {
-      st_stream16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
-    } else {
-      st_stream32(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])),
-                  make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
-    }
-  } else {
-    using E = Elem<__nv_bfloat16>;
-    if constexpr (NP == 4) {
-      st_stream16(p, make_uint4(E::pack2(f[0], f[1]), E::pack2(f[2], f[3]), E::pack2(f[4], f[5]), E::pack2(f[6], f[7])));
-    } else {
-      st_stream32(p, make_uint4(E::pack2(f[0], f[1]), E::pack2(f[2], f[3]), E::pack2(f[4], f[5]), E::pack2(f[6], f[7])),
-                  make_uint4(E::pack2(f[8], f[9]), E::pack2(f[10], f[11]), E::pack2(f[12], f[13]), E::pack2(f[14], f[15])));
-    }
-  }
-}
-
-// N consecutive floats of a streamed-once operand (N = 2, 4, 8), one vector load, no L1 allocation, L2 evict-first
-template <int N>
-__device__ __forceinline__ void ld_stream_vec(const float* p, float (&f)[N]) {
-  static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16, "vector width");
-  if constexpr (N == 1) {
-    f[0] = ld_stream_f1(p);
-  } else if constexpr (N == 2) {
-    const float2 r = ld_stream_f2(p);
-    f[0] = r.x; f[1] = r.y;
-  } else if constexpr (N == 4) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "l"(p), "l"(l2_evict_first_policy()));
-  } else if constexpr (N == 8) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
-                 : "l"(p), "l"(l2_evict_first_policy()));
-  } else {
-    float lo[8], hi[8];
-    ld_stream_vec<8>(p, lo);
-    ld_stream_vec<8>(p + 8, hi);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { f[i] = lo[i]; f[8 + i] = hi[i]; }
-  }
-}
-
-// The reference's arithmetic for one sample, two channels at a time (cuh:80-82, :290):
-//   val = FMUL(w2,v2) -> FFMA(w1,v1,.) -> FFMA(w3,v3,.) -> FFMA(w4,v4,.) ; acc = FFMA(attn, val, acc).
-// Each packed instruction rounds its two elements exactly like the scalar one.
-template <typename T, int VB, int NP>
-__device__ __forceinline__ void accumulate_sample(f32x2 (&acc)[NP], const float4& w, float attn, const RowVec<VB>& q1,
-                                                  const RowVec<VB>& q2, const RowVec<VB>& q3, const RowVec<VB>& q4) {
-  const f32x2 W1 = pk(w.x, w.x), W2 = pk(w.y, w.y), W3 = pk(w.z, w.z), W4 = pk(w.w, w.w), A = pk(attn, attn);
-#pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    f32x2 t = mul2(W2, chan_pair<T, VB>(q2, j));
-    t = fma2(W1, chan_pair<T, VB>(q1, j), t);
-    t = fma2(W3, chan_pair<T, VB>(q3, j), t);
-    t = fma2(W4, chan_pair<T, VB>(q4, j), t);
-    acc[j] = fma2(A, t, acc[j]);
-  }
-}
-
-// Raw operands of one lane's SPL samples between the prefetch and phase 1.
-template <int SPL, int NLV, bool FUSED> struct Prefetched;
-template <int SPL, int NLV> struct Prefetched<SPL, NLV, false> {
-  float xy[2 * SPL];
-  float a[SPL];
-};
-template <int SPL, int NLV> struct Prefetched<SPL, NLV, true> {
-  float off[2 * SPL];
-  float lg[SPL];
-  float4 ref[NLV];
-};
 
 //   T     float | __nv_bfloat16 storage of value/out (arithmetic fp32)
 //   VB    bytes of a value row one lane loads (32: LDG.E.256, 16: LDG.E.128)
@@ -180,6 +38,10 @@ template <int SPL, int NLV> struct Prefetched<SPL, NLV, true> {
 //   NW    warps per CTA ; MINB min CTAs per SM (register budget)
 //   PD    gather pipeline depth in SOURCE order: the corner loads of sample s+PD-1 are issued before sample s is
 //         consumed (ptxas may hoist further: the sample loop is branch-free)
+//   (An L1 prefetch of the corner rows 1-3 samples ahead -- prefetch.global.L1 from four lanes per unit -- was
+//   measured and removed: 545 vs 502 us per 8-frame encoder launch, profiles/r01_s6_sweep_core.log.  So were a
+//   64-register two-record variant (weights precomputed in phase 1: 25 % fewer instructions, one more LDS.128 per
+//   sample: 547 vs 500 us) and a 48-register / 40-warp one (spills: 555 us), profiles/r01_s9_sweep_core.log.)
 template <typename T, int D, int VB, int LPT, int PT, bool FUSED, int NW, int MINB, int PD, bool REC16>
 __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdParams p) {
   constexpr int EB = (int)sizeof(T);
@@ -226,7 +88,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
   __syncthreads();
 
   const int cstride = M * D * EB;                   // bytes between horizontally adjacent pixels
-  const int tiles_per_bm = pyramid ? sTileCum[NL] : (Lq + p.tile_q - 1) / p.tile_q;
+  const int q0 = (!pyramid && p.q_level_begin > 0) ? sStart[p.q_level_begin] : 0;   // first query of the range served
+  const int tiles_per_bm = pyramid ? sTileCum[NL] : (Lq - q0 + p.tile_q - 1) / p.tile_q;
   const long long total_tiles = (long long)p.N * tiles_per_bm * M;
   const int chunks_per_warp = (p.tile_q + NW * UPW - 1) / (NW * UPW);   // warp steps per tile
   // REC16: one record {offset | corner mask, lh, lw, attn}, weights rebuilt in phase 2 (half the record wavefronts on
@@ -283,7 +146,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
       valid = (j < p.tile_q) && (y < sH[t_lvl]) && (x < sW[t_lvl]);
       qi = sStart[t_lvl] + y * sW[t_lvl] + x;
     } else {
-      qi = t_t * p.tile_q + j;
+      qi = q0 + t_t * p.tile_q + j;
       valid = (j < p.tile_q) && (qi < Lq);
     }
     bq = (size_t)t_b * Lq + (valid ? qi : 0);

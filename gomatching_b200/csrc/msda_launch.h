@@ -5,7 +5,7 @@
 
 namespace msda {
 
-enum TileMode { kModeLinear = 1, kModePyramid = 2, kModeGeneric = 3 };
+enum TileMode { kModeLinear = 1, kModePyramid = 2, kModeGeneric = 3, kModeStaged = 4 };
 
 struct FwdParams {
   const void* value;          // (N,S,M,D) fp32 or bf16
@@ -30,6 +30,8 @@ struct FwdParams {
   int variant;                // kernel instantiation
   int force_v1;               // use the runtime-L*P tiled kernel even where the specialised one applies
   int walk;                   // fast kernels: 0 strided heads-fastest tile walk, 1 contiguous raster walk per CTA (diagnostic)
+  int q_level_begin;          // fast kernels, linear mode: only queries >= level_start_index[q_level_begin] (self-attention)
+  int staged_levels;          // staged mode: query levels 0 .. staged_levels-1 run the shared-memory-window kernel
 };
 
 // Each returns a cudaError_t cast to int (0 = ok) or MSDA_E_UNSUPPORTED (-5).
@@ -45,6 +47,9 @@ bool fast_supported(const FwdParams& p);   // shape + the 32-byte operand alignm
 int fast_variant_count();
 int launch_forward_fast_f32(const FwdParams& p, cudaStream_t stream);
 int launch_forward_fast_bf16(const FwdParams& p, cudaStream_t stream);
+// encoder self-attention, fp32: value windows of one query tile staged in shared memory (msda_forward_staged.cu)
+bool staged_supported(const FwdParams& p);
+int launch_forward_staged_f32(const FwdParams& p, cudaStream_t stream);
 // true if the tiled kernels can run this problem (else only the generic kernel can)
 bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused);
 

@@ -121,7 +121,8 @@ def test_setC_default_init_network_capture(setc_cases, tag):
         assert np.array_equal(got[k].cpu().numpy(), ora[k]), k
     if tag == "enc0":      # Lq == S: the pyramid tiling is the default; force the others too
         for tuning in (dict(mode=1), dict(mode=2, tile_h=4, tile_w=4), dict(mode=2, tile_h=16, tile_w=16), dict(mode=3),
-                       dict(mode=2, force_v1=1), dict(mode=2, variant=3), dict(mode=2, variant=5, tile_h=2, tile_w=32)):
+                       dict(mode=2, force_v1=1), dict(mode=2, variant=3), dict(mode=2, variant=5, tile_h=2, tile_w=32),
+                       dict(mode=4), dict(mode=4, tile_h=2), dict(mode=4, tile_h=3)):
             assert np.array_equal(run_core(c, tuning).cpu().numpy(), out), tuning
 
 
@@ -158,6 +159,14 @@ def test_full_size_720p_bit_exact(kind, dist, n):
     out = run_core(c)
     ora = O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"])
     assert np.array_equal(out.cpu().numpy(), ora)
+    if kind == "encoder":   # staged shared-memory-window kernel (windows + global fallback): same bits
+        for tuning in (dict(mode=4), dict(mode=4, tile_h=2)):
+            assert np.array_equal(run_core(c, tuning).cpu().numpy(), ora), tuning
+            fz = g.ms_deform_attn_forward_fused(dev(w.value), dev(w.shapes), dev(w.lsi), dev(w.ref), dev(w.offsets),
+                                                dev(w.logits), tuning=tuning)
+            fz0 = g.ms_deform_attn_forward_fused(dev(w.value), dev(w.shapes), dev(w.lsi), dev(w.ref), dev(w.offsets),
+                                                 dev(w.logits), tuning=dict(mode=1))
+            assert torch.equal(fz, fz0), tuning
     # index parity at full size
     got = g.sample_index(dev(w.loc), dev(w.shapes), dev(w.lsi), 8, 32)
     oi = O.sample_index(c["loc"], c["shapes"], c["lsi"], M=8, D=32)

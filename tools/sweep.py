@@ -48,6 +48,9 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--force-v1", type=int, default=0)
     ap.add_argument("--walk", type=int, default=0)
+    ap.add_argument("--variants", default="", help="comma list; default all")
+    ap.add_argument("--cps", default="", help="comma list of CTAs per SM; default 2,3,4 (quick) or 1..8")
+    ap.add_argument("--top", type=int, default=12)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -69,15 +72,23 @@ def main():
 
     results = []
     variants = range(_native.lib().msda_b200_variant_count())
+    if args.variants:
+        variants = [int(v) for v in args.variants.split(",")]
     cps_list = [1, 2, 3, 4, 6, 8] if not args.quick else [2, 3, 4]
+    if args.cps:
+        cps_list = [int(v) for v in args.cps.split(",")]
     tiles = []
     if args.kind == "encoder":
         tiles += [dict(mode=2, tile_h=h, tile_w=w) for h, w in
                   ([(8, 16), (16, 8), (16, 16), (8, 32), (16, 32)] if args.quick else
                    [(4, 8), (4, 16), (8, 8), (8, 16), (16, 8), (16, 16), (8, 32), (16, 32), (4, 32), (2, 32), (32, 32)])]
     tiles += [dict(mode=1, tile_q=q) for q in ((64, 128, 256) if args.quick else (16, 32, 64, 128, 256))]
-    for v, t, cps in itertools.product(variants, tiles, cps_list):
-        tn = dict(t, variant=v, ctas_per_sm=cps, force_v1=args.force_v1, walk=args.walk)
+    staged = []
+    if args.kind == "encoder" and args.dtype == "f32":   # shared-memory-window kernel: tile_h = query levels staged
+        staged = [dict(mode=4, tile_h=n, variant=0, ctas_per_sm=1, force_v1=0, walk=0) for n in (1, 2, 3)]
+    combos = [dict(t, variant=v, ctas_per_sm=cps, force_v1=args.force_v1, walk=args.walk)
+              for v, t, cps in itertools.product(variants, tiles, cps_list)] + staged
+    for tn in combos:
         try:
             us = time_launches(runner(tn), sets, args.iters)
         except Exception as e:  # noqa: BLE001
@@ -89,7 +100,7 @@ def main():
     print("== %s frames=%d dtype=%s fused=%d dist=%s  B_alg=%.2f MB  sets=%d" % (args.kind, F, args.dtype, args.fused,
                                                                                args.dist, b_alg / 1e6, nsets))
     print("default heuristics: %.2f us  %.0f GB/s" % (base, b_alg / base / 1e3))
-    for r in results[:12]:
+    for r in results[:args.top]:
         print("%8.2f us %7.0f GB/s  %s" % (r["us"], r["gbs"], r["tuning"]))
     print("worst: %.2f us %s" % (results[-1]["us"], results[-1]["tuning"]))
     for v in variants:
