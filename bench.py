@@ -168,7 +168,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def workload_config(args, frames):
@@ -221,6 +221,9 @@ def device_workload(kind, frames, seed, dist, device):
 def algorithmic_bytes(frames, S, Lq):
     v = min(frames * S * M * D, 4 * frames * Lq * M * L * P * D) * 4
     return v + 12 * frames * Lq * M * L * P + 4 * frames * Lq * M * D
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -410,10 +413,21 @@ def main():
         "gpu_launches": world * args.steps * (ENC_LAYERS + DEC_LAYERS), "roofline": roofline, "cpu_baseline": cpu,
         "msda_hbm_gbs": achieved,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _only_json_on_stdout():
+    """Libraries (NCCL prints its version banner on the first communicator) must not add lines to stdout: the driver
+    reads ONE JSON line there.  File descriptor 1 is pointed at stderr for the whole run; the JSON lines go to the
+    saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 if __name__ == "__main__":
+    _JSON_OUT = _only_json_on_stdout()
     main()
