@@ -35,6 +35,7 @@ SYMBOLS = (
     "msda_b200_host_ctx_create",
     "msda_b200_host_ctx_destroy",
     "msda_b200_forward_f32_host",
+    "msda_b200_frames_u8_to_chw_f32",
 )
 
 
@@ -111,6 +112,8 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_linear_f32.argtypes = [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp]
         L.msda_b200_linear_set_trace.restype = None
         L.msda_b200_linear_set_trace.argtypes = [vp]
+        L.msda_b200_frames_u8_to_chw_f32.restype = ci
+        L.msda_b200_frames_u8_to_chw_f32.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp]
         if L.msda_b200_abi_version() != 1:
             raise MSDAError("libmsda_b200.so ABI version mismatch")
         _lib = L

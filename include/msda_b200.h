@@ -195,6 +195,15 @@ int  msda_b200_forward_f32_host(msda_b200_host_ctx_t* ctx,
                                 int N, int S, int M, int D, int L, int Lq, int P,
                                 float* out_host);
 
+/* ---- frame batcher: the input side of the video loop -------------------------------------------------
+ * Replaces, in one pass over HBM, the host-side x.astype("float32").transpose(2, 0, 1) (+ optional channel flip) of
+ * GoMBatchPredictor.__call__ (gomatching/text_track_visualizer.py:313-321) and GoMatching.preprocess_image
+ * (gomatching/modeling/meta_arch/gom_lstmatcher.py:159-170: (x - pixel_mean) / pixel_std, then ImageList.from_tensors
+ * zero padding to Hp x Wp).  frames: device uint8 (N, H, W, 3); mean3 / std3: HOST float[3] in OUTPUT channel order;
+ * out: device float32 (N, 3, Hp, Wp).  Bit-identical to the eager ops (IEEE subtract, then IEEE divide). */
+int msda_b200_frames_u8_to_chw_f32(const unsigned char* frames, int N, int H, int W, int flip_channels,
+                                   const float* mean3, const float* std3, int Hp, int Wp, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
