@@ -67,11 +67,11 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
   int tq = (tn && tn->tile_q > 0) ? tn->tile_q : ((self_attn && elem_bytes == 2) ? 256 : 64);
   int cps = (tn && tn->ctas_per_sm > 0) ? tn->ctas_per_sm : (mode == kModePyramid ? 3 : 4);
   if (mode == kModeStaged) {
-    // staged kernel: one 512-thread CTA per SM; the remaining query levels run 64-query linear tiles (variant 3)
+    // staged kernel: two 256-thread CTAs per SM; the remaining query levels run 64-query linear tiles (variant 3)
     p.staged_levels = (tn && tn->tile_h > 0 && tn->tile_h <= 3) ? tn->tile_h : 1;
     p.tile_q = tq;
     p.tile_h = 0; p.tile_w_log2 = 0;
-    p.grid = sms;
+    p.grid = sms * 2;
     return 0;
   }
   p.tile_w_log2 = ilog2_floor(tw < 4 ? 4 : tw);

@@ -459,7 +459,7 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
     FwdParams rest = p;                                  // the coarser query levels: register-gather kernel
     rest.mode = kModeLinear;
     rest.q_level_begin = p.staged_levels;
-    rest.grid = p.grid * 4;
+    rest.grid = p.grid * 2;                              // 4 CTAs per SM
     rest.variant = 3;
     return launch_forward_fast_f32(rest, stream);
   }

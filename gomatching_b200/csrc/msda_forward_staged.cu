@@ -8,22 +8,28 @@
 // names: put the rows a query tile will touch into shared memory first, asynchronously, and gather from there --
 // LDS has no misses, ~30 clk latency, and the same 128 B/clk pipe.
 //
-// Scheme, per work item = (frame b, head m, tile of TH x TW queries of one pyramid level):
+// Scheme, per work item = (frame b, head m, tile of 8 x 8 queries of pyramid level 0; (8 >> ql) squared for level ql):
 //   1. phase 1 (as in the fast kernel): every lane turns the operands of its 4 samples (one level per lane) into
 //      h_low / w_low / lh / lw / attention; the CTA averages h_low, w_low per sampled level (shared atomics);
-//   2. a window of WH_l x WW_l pixels of this head (128-byte rows) centred on that average is copied per level with
-//      cp.async.cg (16 B per thread, L2 -> shared memory, no register, no L1 allocation); pixels outside the map are
-//      ZERO-FILLED (src-size 0), which is exactly the reference's zero padding (cuh:56-78) -- the gather needs no
-//      corner masks;
+//   2. a window of 20 / 16 / 14 / 13 pixels squared of this head (128-byte rows) centred on that average is copied per
+//      level with cp.async.cg (16 B per thread, L2 -> shared memory, no register, no L1 allocation); pixels outside the
+//      map are ZERO-FILLED (src-size 0), which is exactly the reference's zero padding (cuh:56-78) -- the gather needs no
+//      corner masks.  Two ring slots: A = level 0 then 2, B = level 1 then 3; a slot is refilled while the other's
+//      pass runs.  ~98 KB per CTA, two CTAs per SM;
 //   3. records {window byte offset, lh, lw, attention} go to shared memory; a sample whose 2x2 footprint is not inside
 //      the window keeps the global byte offset + corner mask instead and takes the predicated-LDG path (bit 4 of the
 //      offset word tells which) -- results never depend on where the window sits;
-//   4. four level passes, each after its own cp.async group has landed: per sample one LDS.128 record, eight LDS.128
-//      row halves (4 lanes per unit, immediate offsets for the four corners), the reference's FMUL/FFMA chain in packed
-//      fp32x2, level-major = the reference's accumulation order (cuh:272-296) -> bit-identical outputs;
+//   4. four level passes: per sample one LDS.128 record, eight LDS.128 row halves (4 lanes per unit, immediate offsets
+//      for the four corners), the reference's FMUL/FFMA chain in packed fp32x2, level-major = the reference's
+//      accumulation order (cuh:272-296) -> bit-identical outputs;
 //   5. outputs stored with streaming stores.  The next item's operands are prefetched into registers before the passes.
 // Only query levels whose tiles are worth a window run here (FwdParams::staged_levels); the remaining queries are
 // served by the register-gather kernel in the same stream (msda_forward.cu, launch_forward).
+//
+// Measured (profiles/r01_s16_staged_breakdown.log, r01_s17_*): bit-exact; the gather passes alone run AT the pipe's
+// limit (~1 wavefront/clk/SM), but a work item also pays phase 1 + barriers (144 us per 8-frame launch), the window fill
+// (111 us, and 14.7 M more wavefronts on the same pipe) and the record traffic, and two CTAs per SM overlap little of
+// it: 496 us for the level-0 queries vs ~370 us in the fast kernel.  Opt-in (tuning.mode = 4), not the default.
 #include <type_traits>
 #include "msda_fast_common.cuh"
 #include "msda_launch.h"
@@ -33,20 +39,26 @@ namespace msda {
 
 namespace {
 
-constexpr int kSgWarps = 16, kSgThreads = kSgWarps * 32;
-constexpr int kSgLPR = 4, kSgUPW = 8, kSgUnits = kSgWarps * kSgUPW;   // 128 units per tile
-constexpr int kSgTHlog2 = 3, kSgTWlog2 = 4;                            // level-0 tile: 8 x 16 queries
+constexpr int kSgWarps = 8, kSgThreads = kSgWarps * 32, kSgCtasPerSm = 2;
+constexpr int kSgLPR = 4, kSgUPW = 8, kSgUnits = kSgWarps * kSgUPW;   // 64 units per tile
+constexpr int kSgTHlog2 = 3, kSgTWlog2 = 3;                            // level-0 tile: 8 x 8 queries
 constexpr int kSgL = 4, kSgP = 4, kSgLPT = 16, kSgD = 32;
 constexpr int kRowB = kSgD * 4;                                        // 128-byte value rows
 
-// window extents per sampled level: tile extent at that level + 12 pixels (grid bias up to 4 px + noise, both sides)
+// window extents per sampled level: tile extent at that level + 12 pixels (grid bias up to 4 px + noise, both sides).
+// Two ring slots: A holds level 0, then level 2; B holds level 1, then level 3 -- a window is refilled as soon as its
+// pass is over, while the other slot's pass runs.  ~98 KB per CTA, two CTAs per SM: one CTA's phase 1 / fill latency /
+// barriers overlap the other's gather (measured one CTA per SM: overhead + fill + gather simply add up,
+// profiles/r01_s16_staged_breakdown.log).
 __host__ __device__ constexpr int sg_wh(int l) { return l == 0 ? 20 : l == 1 ? 16 : l == 2 ? 14 : 13; }
-__host__ __device__ constexpr int sg_ww(int l) { return l == 0 ? 28 : l == 1 ? 20 : l == 2 ? 16 : 14; }
+__host__ __device__ constexpr int sg_ww(int l) { return sg_wh(l); }
 __host__ __device__ constexpr int sg_rows(int l) { return sg_wh(l) * sg_ww(l); }
-__host__ __device__ constexpr int sg_woff(int l) { return l == 0 ? 0 : sg_woff(l - 1) + sg_rows(l - 1) * kRowB; }
-constexpr int kSgRecBytes = kSgWarps * kSgLPT * kSgUPW * 16;           // 32 KB
-constexpr int kSgWinBytes = sg_woff(3) + sg_rows(3) * kRowB;           // 164608 B
-constexpr int kSgSmem = kSgRecBytes + kSgWinBytes;
+constexpr int kSgSlotA = (sg_rows(0) > sg_rows(2) ? sg_rows(0) : sg_rows(2)) * kRowB;   // 51200 B
+constexpr int kSgSlotB = (sg_rows(1) > sg_rows(3) ? sg_rows(1) : sg_rows(3)) * kRowB;   // 32768 B
+__host__ __device__ constexpr int sg_woff(int l) { return (l & 1) ? kSgSlotA : 0; }
+constexpr int kSgRecBytes = kSgWarps * kSgLPT * kSgUPW * 16;           // 16 KB
+constexpr int kSgWinBytes = kSgSlotA + kSgSlotB;
+constexpr int kSgSmem = kSgRecBytes + kSgWinBytes;                     // 100352 B
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -59,8 +71,11 @@ template <int OFF> __device__ __forceinline__ uint4 lds128_at(uint32_t a) {
   return r;
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(kSgThreads, 1) msda_fwd_staged_kernel(const FwdParams p) {
+// DBG != 0: diagnostic builds that drop the fallback path / the window fill / the gather passes (wrong results) to
+// attribute the time of a work item (profiles/r01_s16_staged_breakdown.log).
+template <bool FUSED, int DBG>
+__global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kernel(const FwdParams p) {
+  constexpr bool NOFB = (DBG & 1) != 0, NOSTAGE = (DBG & 2) != 0, NOGATHER = (DBG & 4) != 0;   // diagnostics only
   constexpr int NL = kSgL, PT = kSgP, LPT = kSgLPT, SPL = 4, D = kSgD;
   extern __shared__ __align__(128) unsigned char sg_smem[];
   __shared__ int sH[NL], sW[NL], sStart[NL], sTileCum[NL + 1];
@@ -262,23 +277,23 @@ __global__ void __launch_bounds__(kSgThreads, 1) msda_fwd_staged_kernel(const Fw
     }
     if (tid < NL * 4) (&sAcc[parity ^ 1][0][0])[tid] = 0;   // next item's sums (its atomics come after this item's S2)
 
-    // ---------------- stage the four windows: cp.async.cg 16 B per thread, zero-fill outside the map ----------------
-    {
+    // ---------------- window fill: cp.async.cg 16 B per thread, zero-fill outside the map ----------------
+    auto stage = [&](auto level_c) {
+      constexpr int l = decltype(level_c)::value;
       const int c = tid & 7;
-#pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        const int Hs = sH[l], Ws = sW[l], st = sStart[l];
-        const uint32_t dst0 = sWinBase + sg_woff(l) + c * 16;
-        for (int row = tid >> 3; row < sg_rows(l); row += kSgThreads / 8) {
-          const int i = row / sg_ww(l), j = row - i * sg_ww(l);
-          const int h = h0[l] + i, w = w0[l] + j;
-          const bool ok = ((unsigned)h < (unsigned)Hs) && ((unsigned)w < (unsigned)Ws);
-          const char* src = vhead + (ok ? (size_t)(unsigned)((st + h * Ws + w) * cstride) + c * 16 : 0);
-          cp_async16(dst0 + row * kRowB, src, ok ? 16 : 0);
-        }
-        cp_async_commit();
+      const int Hs = sH[l], Ws = sW[l], st = sStart[l];
+      const uint32_t dst0 = sWinBase + sg_woff(l) + c * 16;
+      for (int row = tid >> 3; row < (NOSTAGE ? 0 : sg_rows(l)); row += kSgThreads / 8) {
+        const int i = row / sg_ww(l), j = row - i * sg_ww(l);
+        const int h = h0[l] + i, w = w0[l] + j;
+        const bool ok = ((unsigned)h < (unsigned)Hs) && ((unsigned)w < (unsigned)Ws);
+        const char* src = vhead + (ok ? (size_t)(unsigned)((st + h * Ws + w) * cstride) + c * 16 : 0);
+        cp_async16(dst0 + row * kRowB, src, ok ? 16 : 0);
       }
-    }
+      cp_async_commit();
+    };
+    stage(std::integral_constant<int, 0>{});   // slot A
+    stage(std::integral_constant<int, 1>{});   // slot B
 
     // ---------------- records ----------------
     {
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) msda_fwd_staged_kernel(const Fw
         if (inr) {
           if (inwin) {
             x = (dh * wwk + dw) * kRowB;
-          } else {
+          } else if (!NOFB) {
             const bool top = hl[i] >= 0, bot = hl[i] + 1 <= Hl - 1, lef = wl[i] >= 0, rig = wl[i] + 1 <= Wl - 1;
             const int cmask = (int)(top && lef) | ((int)(top && rig) << 1) | ((int)(bot && lef) << 2) | ((int)(bot && rig) << 3);
             x = ((sStart[k] + hl[i] * Wl + wl[i]) * cstride) | 16 | cmask;   // masked corners are never dereferenced
@@ -321,9 +336,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) msda_fwd_staged_kernel(const Fw
     for (int j = 0; j < 4; ++j) acc[j] = 0ull;
     auto level_pass = [&](auto level_c) {
       constexpr int l = decltype(level_c)::value;
-      cp_async_wait<NL - 1 - l>();
-      __syncthreads();   // S2..S5: every thread's share of window l has landed; (l == 0) records visible
-      if (warp_active) {
+      if (warp_active && !NOGATHER) {
         const uint32_t wbase = sWinBase + sg_woff(l) + c0;
         const int rs = sW[l] * cstride;             // fallback: bytes between vertically adjacent pixels
 #pragma unroll
@@ -332,7 +345,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) msda_fwd_staged_kernel(const Fw
           const float4 r = sRec[s * kSgUPW + (g ^ (2 * l))];
           const int x = __float_as_int(r.x);
           RowVec<32> q[4];
-          if (!(x & 16)) {
+          if (NOFB || !(x & 16)) {
             const uint32_t a0 = wbase + (uint32_t)x, a1 = a0 + (uint32_t)dhi;
             q[0].lo = lds128_at<0>(a0);                             q[0].hi = lds128_at<0>(a1);
             q[1].lo = lds128_at<kRowB>(a0);                         q[1].hi = lds128_at<kRowB>(a1);
@@ -355,9 +368,19 @@ __global__ void __launch_bounds__(kSgThreads, 1) msda_fwd_staged_kernel(const Fw
         }
       }
     };
+    cp_async_wait<1>();
+    __syncthreads();   // S2: level 0 has landed (every thread's share); records visible
     level_pass(std::integral_constant<int, 0>{});
+    cp_async_wait<0>();
+    __syncthreads();   // S3: pass 0 is over everywhere (slot A free) and level 1 has landed
+    stage(std::integral_constant<int, 2>{});   // slot A, fills while pass 1 runs
     level_pass(std::integral_constant<int, 1>{});
+    cp_async_wait<0>();
+    __syncthreads();   // S4: slot B free, level 2 landed
+    stage(std::integral_constant<int, 3>{});   // slot B, fills while pass 2 runs
     level_pass(std::integral_constant<int, 2>{});
+    cp_async_wait<0>();
+    __syncthreads();   // S5: level 3 landed
     level_pass(std::integral_constant<int, 3>{});
     if (valid) {
       char* op = reinterpret_cast<char*>(p.out) + unit * (size_t)(D * 4);
@@ -367,19 +390,20 @@ __global__ void __launch_bounds__(kSgThreads, 1) msda_fwd_staged_kernel(const Fw
       st_stream16(op + c0, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
       st_stream16(op + c0 + dhi, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
     }
-    __syncthreads();   // S6: windows and records may be overwritten
+    __syncthreads();   // S6: slots and records may be overwritten
     item = next_item;
     parity ^= 1;
   }
 }
 
-template <bool FUSED>
+template <bool FUSED, int DBG>
 int launch_staged(const FwdParams& p, cudaStream_t stream) {
-  auto kern = msda_fwd_staged_kernel<FUSED>;
+  auto kern = msda_fwd_staged_kernel<FUSED, DBG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmem);
     if (e != cudaSuccess) return (int)e;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // two ~98 KB CTAs per SM
     configured = true;
   }
   kern<<<p.grid, kSgThreads, kSgSmem, stream>>>(p);
@@ -394,7 +418,13 @@ bool staged_supported(const FwdParams& p) {
 }
 
 int launch_forward_staged_f32(const FwdParams& p, cudaStream_t stream) {
-  return p.loc == nullptr ? launch_staged<true>(p, stream) : launch_staged<false>(p, stream);
+  if (p.loc != nullptr) {   // diagnostic variants (wrong results) exist for the core operator only
+    if (p.variant == 1) return launch_staged<false, 1>(p, stream);    // no fallback path
+    if (p.variant == 2) return launch_staged<false, 3>(p, stream);    // ... and no window fill
+    if (p.variant == 3) return launch_staged<false, 5>(p, stream);    // ... no gather passes (fill only)
+    if (p.variant == 4) return launch_staged<false, 7>(p, stream);    // ... neither: phase 1, records, barriers, stores
+  }
+  return p.loc == nullptr ? launch_staged<true, 0>(p, stream) : launch_staged<false, 0>(p, stream);
 }
 
 }  // namespace msda
