@@ -41,7 +41,10 @@ namespace msda {
 //   (An L1 prefetch of the corner rows 1-3 samples ahead -- prefetch.global.L1 from four lanes per unit -- was
 //   measured and removed: 545 vs 502 us per 8-frame encoder launch, profiles/r01_s6_sweep_core.log.  So were a
 //   64-register two-record variant (weights precomputed in phase 1: 25 % fewer instructions, one more LDS.128 per
-//   sample: 547 vs 500 us) and a 48-register / 40-warp one (spills: 555 us), profiles/r01_s9_sweep_core.log.)
+//   sample: 547 vs 500 us) and a 48-register / 40-warp one (spills: 555 us), profiles/r01_s9_sweep_core.log; and a
+//   WINDOW prefetch -- one prefetch.global.L1 per row of the tile's level-(l+1) window, issued by the whole CTA a level
+//   pass ahead, one 8x16 tile per 32-warp CTA: 682 vs 543 us for the same shape without it,
+//   profiles/r01_s18_sweep_window_prefetch.log.  L1 prefetches are not free on this part.)
 template <typename T, int D, int VB, int LPT, int PT, bool FUSED, int NW, int MINB, int PD, bool REC16>
 __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdParams p) {
   constexpr int EB = (int)sizeof(T);
