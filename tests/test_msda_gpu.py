@@ -214,6 +214,36 @@ def test_1080p_encoder_properties():
     assert torch.equal(o1.view(2, -1, 8, 32)[..., :1].expand(-1, -1, -1, 32), o1.view(2, -1, 8, 32))
 
 
+@pytest.mark.parametrize("hw,n,dist", [((720, 1280), 1, "uniform"), ((1080, 1920), 1, "local"), ((192, 320), 3, "local"),
+                                       ((96, 96), 2, "uniform")])
+def test_staged_window_kernel_is_bit_identical(hw, n, dist):
+    """tuning.mode = 4 (value windows in shared memory, msda_forward_staged.cu): window placement, zero-filled borders
+    and the global fallback for samples outside a window never change a bit -- uniform locations put most samples
+    outside the windows, tiny maps make windows larger than the map, box reference points use the other offset rule."""
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("encoder", hw[0], hw[1], n=n, seed=21, dist=dist)
+    v, sh, ls, loc, at = dev(w.value), dev(w.shapes), dev(w.lsi), dev(w.loc), dev(w.attn)
+    base = g.ms_deform_attn_forward(v, sh, ls, loc, at, 64, tuning=dict(mode=1))
+    rf, off, lg = dev(w.ref), dev(w.offsets), dev(w.logits)
+    fbase = g.ms_deform_attn_forward_fused(v, sh, ls, rf, off, lg, tuning=dict(mode=1))
+    box = torch.cat([rf, torch.full_like(rf, 0.05)], -1).contiguous()             # (N, Lq, L, 4): centre + (w, h)
+    bbase = g.ms_deform_attn_forward_fused(v, sh, ls, box, off, lg, tuning=dict(mode=1))
+    for levels in (1, 2, 3):
+        tn = dict(mode=4, tile_h=levels)
+        assert torch.equal(g.ms_deform_attn_forward(v, sh, ls, loc, at, 64, tuning=tn), base), tn
+        assert torch.equal(g.ms_deform_attn_forward_fused(v, sh, ls, rf, off, lg, tuning=tn), fbase), tn
+        assert torch.equal(g.ms_deform_attn_forward_fused(v, sh, ls, box, off, lg, tuning=tn), bbase), tn
+    # decoder shapes (Lq != S) and bf16 storage fall back to the register-gather kernel under the same tuning
+    d = syn.make_workload("decoder", 192, 320, n=1, seed=2, dist="local")
+    a = g.ms_deform_attn_forward(dev(d.value), dev(d.shapes), dev(d.lsi), dev(d.loc), dev(d.attn), 64, tuning=dict(mode=4))
+    b = g.ms_deform_attn_forward(dev(d.value), dev(d.shapes), dev(d.lsi), dev(d.loc), dev(d.attn), 64)
+    assert torch.equal(a, b)
+    vb = v.to(torch.bfloat16)
+    assert torch.equal(g.ms_deform_attn_forward(vb, sh, ls, loc, at, 64, tuning=dict(mode=4)),
+                       g.ms_deform_attn_forward(vb, sh, ls, loc, at, 64))
+
+
 # ---------------------------------------------------------------------------------------------------
 # Fused glue: softmax + offsets->locations inside the sampler
 # ---------------------------------------------------------------------------------------------------
