@@ -47,7 +47,7 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
   const bool can_tile = tiled_supported(elem_bytes, p.D, p.L, p.P, fused);
   int mode = tn ? tn->mode : 0;
   const bool self_attn = p.Lq == p.S;
-  // defaults from the B200 sweeps (profiles/r01_sweep_s4_*.log): 2-D pyramid tiles only pay for the fp32 core
+  // defaults from the B200 sweeps (profiles/r01_s9_sweep_*.log, r01_s12_sweep_*.log): 2-D pyramid tiles only pay for the fp32 core
   // operator in encoder self-attention; everything else runs linear query tiles
   if (mode == 0) mode = !can_tile ? kModeGeneric : ((self_attn && elem_bytes == 4 && !fused) ? kModePyramid : kModeLinear);
   if (mode == kModePyramid && !self_attn) mode = kModeLinear;
