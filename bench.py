@@ -389,6 +389,12 @@ def main():
                 "algorithmic_bytes_per_launch": b_alg, "mean_launch_us": enc_mean_ms * 1e3,
                 "launches_timed": len(enc_ms), "peak_source": peak_src,
                 "gather_bytes_per_launch": 4 * F * enc[0]["Lq"] * M * L * P * D * 4}
+    # secondary bound: the SM's L1 data pipe returns at most one 128-byte row per clock per SM
+    if clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        rows = 4 * F * enc[0]["Lq"] * M * L * P
+        roofline["l1_pipe"] = {"bound": "l1 data pipe (1 row/clk/SM)", "unit": "rows/clk/SM", "peak": 1.0,
+                               "achieved": rows / (enc_mean_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sms)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
