@@ -36,6 +36,7 @@ SYMBOLS = (
     "msda_b200_host_ctx_destroy",
     "msda_b200_forward_f32_host",
     "msda_b200_frames_u8_to_chw_f32",
+    "msda_b200_staged_set_host_shapes",
 )
 
 
@@ -112,6 +113,8 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_linear_f32.argtypes = [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp]
         L.msda_b200_linear_set_trace.restype = None
         L.msda_b200_linear_set_trace.argtypes = [vp]
+        L.msda_b200_staged_set_host_shapes.restype = None
+        L.msda_b200_staged_set_host_shapes.argtypes = [vp, vp, ci]
         L.msda_b200_frames_u8_to_chw_f32.restype = ci
         L.msda_b200_frames_u8_to_chw_f32.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp]
         if L.msda_b200_abi_version() != 1:
@@ -124,6 +127,30 @@ def check(rc: int, what: str = "msda_b200") -> None:
     if rc != 0:
         msg = lib().msda_b200_error_string(int(rc))
         raise MSDAError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+_shape_hint_cache = {}
+
+
+def staged_shape_hint(spatial_shapes, level_start_index) -> None:
+    """tuning mode 4: hand the level geometry to the library as host arrays so its window fills can use TMA.
+    One device->host read per distinct shapes tensor (keyed by storage pointer and version), none afterwards."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version)
+    hit = _shape_hint_cache.get(key)
+    if hit is None:
+        if len(_shape_hint_cache) > 64:
+            _shape_hint_cache.clear()
+        sh = spatial_shapes.detach().to("cpu", copy=True).to(dtype=__import__("torch").int64).contiguous()
+        ls = level_start_index.detach().to("cpu", copy=True).to(dtype=__import__("torch").int64).contiguous()
+        hit = _shape_hint_cache[key] = (sh, ls)
+    sh, ls = hit
+    lib().msda_b200_staged_set_host_shapes(sh.data_ptr(), ls.data_ptr(), int(ls.numel()))
+
+
+def tuning_mode(tuning) -> int:
+    if tuning is None:
+        return 0
+    return int(tuning.mode) if isinstance(tuning, Tuning) else int(dict(tuning).get("mode", 0))
 
 
 def make_tuning(tuning) -> "ctypes.POINTER(Tuning) | None":

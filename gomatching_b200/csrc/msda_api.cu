@@ -145,6 +145,10 @@ const char* msda_b200_error_string(int code) {
 int msda_b200_sm_count(void) { return sm_count_current(); }
 int msda_b200_variant_count(void) { return forward_variant_count(); }
 
+void msda_b200_staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host, int L) {
+  staged_set_host_shapes(shapes_host, lsi_host, L);
+}
+
 int msda_b200_forward_f32(const float* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
                           const float* attn, int N, int S, int M, int D, int L, int Lq, int P, float* out,
                           void* stream) {

@@ -26,13 +26,22 @@
 // Only query levels whose tiles are worth a window run here (FwdParams::staged_levels); the remaining queries are
 // served by the register-gather kernel in the same stream (msda_forward.cu, launch_forward).
 //
-// Measured (profiles/r01_s16_staged_breakdown.log, r01_s17_*): bit-exact; the gather passes alone run AT the pipe's
-// limit (~1 wavefront/clk/SM), but a work item also pays phase 1 + barriers (144 us per 8-frame launch), the window fill
-// (111 us, and 14.7 M more wavefronts on the same pipe) and the record traffic, and two CTAs per SM overlap little of
-// it: 496 us for the level-0 queries vs ~370 us in the fast kernel.  Opt-in (tuning.mode = 4), not the default.
+// Window fills: with the level shapes known on the host (msda_b200_staged_set_host_shapes; the Python wrapper reads
+// them once per shapes tensor) each window is ONE 5-D TMA tile load (value viewed as (N, H_l, W_l, M, D), box
+// {D, 1 head, WW, WH, 1 frame}, out-of-map pixels zero-filled by the TMA unit) completing on the slot's mbarrier --
+// off the LSU pipe and off the threads; otherwise cp.async as described above.
+//
+// Measured (profiles/r01_s16_*, r01_s17_*, r01_s21_staged_tma_breakdown.log, r01_s22_*): bit-exact; the gather passes run
+// AT the pipe's limit (~1 wavefront/clk/SM; 201 us per 8-frame launch for the 59 M rows of the level-0 queries), the
+// TMA fills hide almost completely (+34 us; cp.async fills cost +111 us and 14.7 M wavefronts on the same pipe), but
+// phase 1 + barriers + records (133 us) and the divergent fallback branch (33 us) do not: 390 us for the level-0
+// queries vs ~370 us in the fast kernel, 515 vs 494 us per launch (571 vs 543 fused).  Opt-in (tuning.mode = 4).
+#include <cuda.h>
+#include <mutex>
 #include <type_traits>
 #include "msda_fast_common.cuh"
 #include "msda_launch.h"
+#include <string.h>
 #include "../../include/msda_b200.h"
 
 namespace msda {
@@ -64,6 +73,22 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int sr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// ---- TMA window fill (used when the level shapes are known on the host: msda_b200_staged_set_host_shapes) ----
+struct StagedMaps { CUtensorMap lv[kSgL]; };
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nSG_WAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra SG_WAIT_DONE;\nbra SG_WAIT_LOOP;\nSG_WAIT_DONE:\n}\n" ::"r"(bar),
+      "r"(parity) : "memory");
+}
+// value viewed as (N, H_l, W_l, M, D): box = {D, 1 head, WW, WH, 1 frame}; out-of-map pixels arrive as zeros
+__device__ __forceinline__ void tma_window(uint32_t dst, const CUtensorMap* map, uint32_t bar, int m, int w0, int h0, int b) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(0), "r"(m), "r"(w0), "r"(h0), "r"(b) : "memory");
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int OFF> __device__ __forceinline__ uint4 lds128_at(uint32_t a) {
   uint4 r;
@@ -73,14 +98,15 @@ template <int OFF> __device__ __forceinline__ uint4 lds128_at(uint32_t a) {
 
 // DBG != 0: diagnostic builds that drop the fallback path / the window fill / the gather passes (wrong results) to
 // attribute the time of a work item (profiles/r01_s16_staged_breakdown.log).
-template <bool FUSED, int DBG>
-__global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kernel(const FwdParams p) {
+template <bool FUSED, int DBG, bool TMA>
+__global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kernel(const FwdParams p, const __grid_constant__ StagedMaps maps) {
   constexpr bool NOFB = (DBG & 1) != 0, NOSTAGE = (DBG & 2) != 0, NOGATHER = (DBG & 4) != 0;   // diagnostics only
   constexpr int NL = kSgL, PT = kSgP, LPT = kSgLPT, SPL = 4, D = kSgD;
   extern __shared__ __align__(128) unsigned char sg_smem[];
   __shared__ int sH[NL], sW[NL], sStart[NL], sTileCum[NL + 1];
   __shared__ float sHf[NL], sWf[NL];
-  __shared__ int sAcc[2][NL][4];          // per sampled level: sum h_low, sum w_low, count (double-buffered by item parity)
+  __shared__ int sAcc[2][NL][4];
+  __shared__ __align__(8) unsigned long long sBar[2];   // TMA: one mbarrier per ring slot, two fills per item each          // per sampled level: sum h_low, sum w_low, count (double-buffered by item parity)
 
   const int M = p.M, Lq = p.Lq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,6 +119,11 @@ __global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kern
     sWf[tid] = (float)sW[tid];
   }
   if (tid < 2 * NL * 4) (&sAcc[0][0][0])[tid] = 0;
+  if (TMA && tid == 0) {
+    mbar_init((uint32_t)__cvta_generic_to_shared(&sBar[0]), 1);
+    mbar_init((uint32_t)__cvta_generic_to_shared(&sBar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const int QL = p.staged_levels;          // query levels served here (tiles of level ql: (8 >> ql) x (16 >> ql))
   if (tid == 0) {
@@ -280,6 +311,14 @@ __global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kern
     // ---------------- window fill: cp.async.cg 16 B per thread, zero-fill outside the map ----------------
     auto stage = [&](auto level_c) {
       constexpr int l = decltype(level_c)::value;
+      if constexpr (TMA) {
+        if (tid == 0 && !NOSTAGE) {
+          const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sBar[l & 1]);
+          mbar_expect_tx(bar, sg_rows(l) * kRowB);
+          tma_window(sWinBase + sg_woff(l), &maps.lv[l], bar, cur.m, w0[l], h0[l], cur.b);
+        }
+        return;
+      }
       const int c = tid & 7;
       const int Hs = sH[l], Ws = sW[l], st = sStart[l];
       const uint32_t dst0 = sWinBase + sg_woff(l) + c * 16;
@@ -368,20 +407,42 @@ __global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kern
         }
       }
     };
-    cp_async_wait<1>();
-    __syncthreads();   // S2: level 0 has landed (every thread's share); records visible
-    level_pass(std::integral_constant<int, 0>{});
-    cp_async_wait<0>();
-    __syncthreads();   // S3: pass 0 is over everywhere (slot A free) and level 1 has landed
-    stage(std::integral_constant<int, 2>{});   // slot A, fills while pass 1 runs
-    level_pass(std::integral_constant<int, 1>{});
-    cp_async_wait<0>();
-    __syncthreads();   // S4: slot B free, level 2 landed
-    stage(std::integral_constant<int, 3>{});   // slot B, fills while pass 2 runs
-    level_pass(std::integral_constant<int, 2>{});
-    cp_async_wait<0>();
-    __syncthreads();   // S5: level 3 landed
-    level_pass(std::integral_constant<int, 3>{});
+    // landed(slot, n): the n-th fill (0, 1) of this item into ring slot A (0) / B (1) is complete and visible
+    auto landed = [&](int slot, uint32_t nth) {
+      if constexpr (TMA) {
+        if (!NOSTAGE) mbar_wait((uint32_t)__cvta_generic_to_shared(&sBar[slot]), nth);
+      }
+    };
+    if constexpr (TMA) {
+      __syncwarp();      // records were written by this warp
+      landed(0, 0);
+      level_pass(std::integral_constant<int, 0>{});
+      __syncthreads();   // S3: pass 0 is over everywhere (slot A free)
+      stage(std::integral_constant<int, 2>{});
+      landed(1, 0);
+      level_pass(std::integral_constant<int, 1>{});
+      __syncthreads();   // S4: slot B free
+      stage(std::integral_constant<int, 3>{});
+      landed(0, 1);
+      level_pass(std::integral_constant<int, 2>{});
+      landed(1, 1);
+      level_pass(std::integral_constant<int, 3>{});
+    } else {
+      cp_async_wait<1>();
+      __syncthreads();   // S2: level 0 has landed (every thread's share); records visible
+      level_pass(std::integral_constant<int, 0>{});
+      cp_async_wait<0>();
+      __syncthreads();   // S3: pass 0 is over everywhere (slot A free) and level 1 has landed
+      stage(std::integral_constant<int, 2>{});   // slot A, fills while pass 1 runs
+      level_pass(std::integral_constant<int, 1>{});
+      cp_async_wait<0>();
+      __syncthreads();   // S4: slot B free, level 2 landed
+      stage(std::integral_constant<int, 3>{});   // slot B, fills while pass 2 runs
+      level_pass(std::integral_constant<int, 2>{});
+      cp_async_wait<0>();
+      __syncthreads();   // S5: level 3 landed
+      level_pass(std::integral_constant<int, 3>{});
+    }
     if (valid) {
       char* op = reinterpret_cast<char*>(p.out) + unit * (size_t)(D * 4);
       float f[8];
@@ -396,9 +457,58 @@ __global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kern
   }
 }
 
-template <bool FUSED, int DBG>
-int launch_staged(const FwdParams& p, cudaStream_t stream) {
-  auto kern = msda_fwd_staged_kernel<FUSED, DBG>;
+// ---- host side ------------------------------------------------------------------------------------------
+struct HostShapes { bool valid = false; long long hw[kSgL][2]; long long lsi[kSgL]; };
+HostShapes g_host_shapes;
+std::mutex g_host_shapes_mutex;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn staged_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// One 5-D map per sampled level over value (N, S, M, D) fp32: (D, M, W_l, H_l, N), base at the level's first pixel.
+bool make_window_maps(const FwdParams& p, StagedMaps& maps) {
+  HostShapes hs;
+  {
+    std::lock_guard<std::mutex> lock(g_host_shapes_mutex);
+    hs = g_host_shapes;
+  }
+  EncodeTiledFn fn = staged_encode_fn();
+  if (!hs.valid || !fn) return false;
+  long long total = 0;
+  for (int l = 0; l < kSgL; ++l) total += hs.hw[l][0] * hs.hw[l][1];
+  if (total != p.S) return false;                          // the hint belongs to another pyramid
+  const cuuint64_t row = (cuuint64_t)p.D * 4, px = (cuuint64_t)p.M * row;
+  for (int l = 0; l < kSgL; ++l) {
+    const cuuint64_t H = (cuuint64_t)hs.hw[l][0], W = (cuuint64_t)hs.hw[l][1];
+    cuuint64_t gdim[5] = {(cuuint64_t)p.D, (cuuint64_t)p.M, W, H, (cuuint64_t)p.N};
+    cuuint64_t gstride[4] = {row, px, W * px, (cuuint64_t)p.S * px};
+    cuuint32_t box[5] = {(cuuint32_t)p.D, 1, (cuuint32_t)sg_ww(l), (cuuint32_t)sg_wh(l), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = const_cast<char*>(reinterpret_cast<const char*>(p.value) + (size_t)hs.lsi[l] * px);
+    if (fn(&maps.lv[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
+template <bool FUSED, int DBG, bool TMA>
+int launch_staged_impl(const FwdParams& p, const StagedMaps& maps, cudaStream_t stream) {
+  auto kern = msda_fwd_staged_kernel<FUSED, DBG, TMA>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmem);
@@ -406,8 +516,16 @@ int launch_staged(const FwdParams& p, cudaStream_t stream) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // two ~98 KB CTAs per SM
     configured = true;
   }
-  kern<<<p.grid, kSgThreads, kSgSmem, stream>>>(p);
+  kern<<<p.grid, kSgThreads, kSgSmem, stream>>>(p, maps);
   return (int)cudaGetLastError();
+}
+
+template <bool FUSED, int DBG>
+int launch_staged(const FwdParams& p, cudaStream_t stream) {
+  StagedMaps maps;
+  if (p.walk != 1 && make_window_maps(p, maps)) return launch_staged_impl<FUSED, DBG, true>(p, maps, stream);   // walk = 1: force cp.async fills
+  memset(&maps, 0, sizeof(maps));
+  return launch_staged_impl<FUSED, DBG, false>(p, maps, stream);
 }
 
 }  // namespace
@@ -415,6 +533,18 @@ int launch_staged(const FwdParams& p, cudaStream_t stream) {
 bool staged_supported(const FwdParams& p) {
   return p.Lq == p.S && p.D == 32 && p.L == 4 && p.P == 4 && fast_supported(p) &&
          (long long)p.N * p.M * ((long long)p.S / 4 + 64) < (1ll << 31);
+}
+
+void staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host, int L) {
+  std::lock_guard<std::mutex> lock(g_host_shapes_mutex);
+  g_host_shapes.valid = false;
+  if (!shapes_host || !lsi_host || L != kSgL) return;
+  for (int l = 0; l < kSgL; ++l) {
+    g_host_shapes.hw[l][0] = shapes_host[2 * l];
+    g_host_shapes.hw[l][1] = shapes_host[2 * l + 1];
+    g_host_shapes.lsi[l] = lsi_host[l];
+  }
+  g_host_shapes.valid = true;
 }
 
 int launch_forward_staged_f32(const FwdParams& p, cudaStream_t stream) {

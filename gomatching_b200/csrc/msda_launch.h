@@ -50,6 +50,8 @@ int launch_forward_fast_bf16(const FwdParams& p, cudaStream_t stream);
 // encoder self-attention, fp32: value windows of one query tile staged in shared memory (msda_forward_staged.cu)
 bool staged_supported(const FwdParams& p);
 int launch_forward_staged_f32(const FwdParams& p, cudaStream_t stream);
+// optional: level shapes on the host let the staged kernel fill its windows with TMA (tensor maps need them)
+void staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host, int L);
 // true if the tiled kernels can run this problem (else only the generic kernel can)
 bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused);
 

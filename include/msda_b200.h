@@ -75,6 +75,11 @@ const char* msda_b200_error_string(int code);
 /* number of SMs of the current device, or a negative error */
 int         msda_b200_sm_count(void);
 int         msda_b200_variant_count(void);
+/* Optional hint for tuning.mode = 4: the (H_l, W_l) pairs and level start indices as HOST arrays (L = 4).  With it the
+ * staged kernel fills its shared-memory windows with TMA (the tensor maps are encoded on the host and need the level
+ * geometry, which the operator API only hands over as a device tensor: ms_deform_attn.py:117-123); without it, or if
+ * the hint does not match S, the windows are filled with cp.async.  Pass NULL to clear.  Process-wide, thread-safe. */
+void        msda_b200_staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host, int L);
 
 /* ---- core operator: the _MSDeformAttnFunction boundary (ms_deform_attn.py:20-27) ------------------ */
 int msda_b200_forward_f32(const float* value, const int64_t* shapes, const int64_t* lsi,
