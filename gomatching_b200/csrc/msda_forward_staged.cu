@@ -36,6 +36,7 @@
 // TMA fills hide almost completely (+34 us; cp.async fills cost +111 us and 14.7 M wavefronts on the same pipe), but
 // phase 1 + barriers + records (133 us) and the divergent fallback branch (33 us) do not: 390 us for the level-0
 // queries vs ~370 us in the fast kernel, 515 vs 494 us per launch (571 vs 543 fused).  Opt-in (tuning.mode = 4).
+// (A head start of 1-8 us for one of the two co-resident CTAs -- in case they ran in lockstep -- changes nothing.)
 #include <cuda.h>
 #include <mutex>
 #include <type_traits>
