@@ -6,17 +6,19 @@ Public surface (mirrors third_party/adet/layers/ms_deform_attn.py of the referen
     ms_deform_attn_forward       adet._C.ms_deform_attn_forward drop-in
     ms_deform_attn_backward      adet._C.ms_deform_attn_backward drop-in
     ms_deform_attn_forward_fused softmax + offsets->locations + sampler in one kernel
+    DeformableTransformerEncoderLayer  encoder layer drop-in (sampler + tensor-core feed-forward block)
     install_into_adet            monkey-patch the reference's import sites
 """
 from .ms_deform_attn_func import (MSDeformAttnFunction, _MSDeformAttnFunction, fused_supported, locations_softmax,
                                   ms_deform_attn_backward, ms_deform_attn_forward, ms_deform_attn_forward_fused,
                                   sample_index)
 from .ms_deform_attn import MSDeformAttn
+from .encoder_layer import DeformableTransformerEncoderLayer
 
 __all__ = [
     "MSDeformAttn", "MSDeformAttnFunction", "_MSDeformAttnFunction", "ms_deform_attn_forward",
     "ms_deform_attn_backward", "ms_deform_attn_forward_fused", "fused_supported", "sample_index",
-    "locations_softmax", "install_into_adet",
+    "locations_softmax", "install_into_adet", "DeformableTransformerEncoderLayer",
 ]
 
 
@@ -26,6 +28,7 @@ def install_into_adet():
     * ``adet._C.ms_deform_attn_forward/backward``  (csrc/vision.cpp:52-55) -> the C-ABI kernels
     * ``adet.layers.ms_deform_attn.MSDeformAttn`` and ``adet.layers.deformable_transformer.MSDeformAttn``
       (deformable_transformer.py:16) -> :class:`MSDeformAttn`
+    * ``adet.layers.deformable_transformer.DeformableTransformerEncoderLayer`` (:218) -> the drop-in layer
     Call after ``adet`` is importable; modules that are not imported yet are skipped.
     """
     import sys
@@ -43,4 +46,6 @@ def install_into_adet():
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "MSDeformAttn"):
             mod.MSDeformAttn = MSDeformAttn
+        if mod is not None and hasattr(mod, "DeformableTransformerEncoderLayer"):
+            mod.DeformableTransformerEncoderLayer = DeformableTransformerEncoderLayer
     return c

@@ -26,6 +26,7 @@ SYMBOLS = (
     "msda_b200_forward_fused_bf16",
     "msda_b200_linear_split_weight_f32",
     "msda_b200_linear_f32",
+    "msda_b200_linear_relu_f32",
     "msda_b200_linear_set_trace",
     "msda_b200_forward_fused_pitched_f32",
     "msda_b200_forward_fused_pitched_bf16",
@@ -111,6 +112,8 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_linear_split_weight_f32.argtypes = [vp, ci, ci, vp, vp, vp]
         L.msda_b200_linear_f32.restype = ci
         L.msda_b200_linear_f32.argtypes = [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp]
+        L.msda_b200_linear_relu_f32.restype = ci
+        L.msda_b200_linear_relu_f32.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, vp, ci, vp]
         L.msda_b200_linear_set_trace.restype = None
         L.msda_b200_linear_set_trace.argtypes = [vp]
         L.msda_b200_staged_set_host_shapes.restype = None

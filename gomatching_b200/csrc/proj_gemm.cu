@@ -122,6 +122,7 @@ struct GemmParams {
   int ldy;
   const float* bias;             // [N] or nullptr
   const unsigned char* row_zero; // [M] or nullptr: rows written as 0 (padding mask, ms_deform_attn.py:135)
+  int relu;                      // epilogue: y = max(y, 0) after the bias (encoder FFN linear1 + activation, deformable_transformer.py:249)
   int M, N, K;
   int block_n;                   // columns per CTA (multiple of 32, <= 256)
   int tmem_cols;                 // power of two >= block_n
@@ -284,6 +285,10 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
             const float4 bj = *reinterpret_cast<const float4*>(&s_bias[c * 32 + 4 * j]);
             float f[4] = {__fadd_rn(__uint_as_float(v[4 * j + 0]), bj.x), __fadd_rn(__uint_as_float(v[4 * j + 1]), bj.y),
                           __fadd_rn(__uint_as_float(v[4 * j + 2]), bj.z), __fadd_rn(__uint_as_float(v[4 * j + 3]), bj.w)};
+            if (p.relu) {                         // x < 0 ? 0 : x keeps NaN like torch.relu
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[e] = f[e] < 0.0f ? 0.0f : f[e];
+            }
             if (zero_row) f[0] = f[1] = f[2] = f[3] = 0.0f;
             const uint32_t dst = slab + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) * 16);
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
@@ -386,8 +391,8 @@ int msda_b200_linear_split_weight_f32(const float* w, int N, int K, float* w_hi,
   return (int)cudaGetLastError();
 }
 
-int msda_b200_linear_f32(const float* x, int ldx, const float* w_hi, const float* w_lo, const float* bias,
-                         const unsigned char* row_zero, int M, int N, int K, float* y, int ldy, void* stream) {
+static int linear_impl(const float* x, int ldx, const float* w_hi, const float* w_lo, const float* bias,
+                       const unsigned char* row_zero, int M, int N, int K, float* y, int ldy, void* stream, int relu) {
   using namespace msda;
   if (!x || !w_hi || !w_lo || !y) return MSDA_E_NULLPTR;
   if (M <= 0 || N <= 0 || K <= 0) return MSDA_E_DIMS;
@@ -417,7 +422,7 @@ int msda_b200_linear_f32(const float* x, int ldx, const float* w_hi, const float
 
   GemmParams p;
   p.trace = g_trace;
-  p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K; p.block_n = BN; p.tmem_cols = tmem_cols;
+  p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K; p.block_n = BN; p.tmem_cols = tmem_cols; p.relu = relu;
   const int stages = two ? 3 : 2;
   const size_t stage_bytes = 2 * (size_t)kSubBytes * (two ? 2 : 1) + 2 * (size_t)BN * kBlockK * 4;
   size_t smem = stages * stage_bytes;
@@ -436,6 +441,16 @@ int msda_b200_linear_f32(const float* x, int ldx, const float* w_hi, const float
   else
     proj_gemm_3xtf32_kernel<1, 2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_y, p);
   return (int)cudaGetLastError();
+}
+
+int msda_b200_linear_f32(const float* x, int ldx, const float* w_hi, const float* w_lo, const float* bias,
+                         const unsigned char* row_zero, int M, int N, int K, float* y, int ldy, void* stream) {
+  return linear_impl(x, ldx, w_hi, w_lo, bias, row_zero, M, N, K, y, ldy, stream, 0);
+}
+
+int msda_b200_linear_relu_f32(const float* x, int ldx, const float* w_hi, const float* w_lo, const float* bias,
+                              int M, int N, int K, float* y, int ldy, void* stream) {
+  return linear_impl(x, ldx, w_hi, w_lo, bias, nullptr, M, N, K, y, ldy, stream, 1);
 }
 
 }  // extern "C"

@@ -38,11 +38,13 @@ def split_weight(weight: torch.Tensor):
 
 
 def linear_3xtf32(x: torch.Tensor, weight: torch.Tensor, bias: "torch.Tensor | None" = None,
-                  row_zero: "torch.Tensor | None" = None, out: "torch.Tensor | None" = None) -> torch.Tensor:
+                  row_zero: "torch.Tensor | None" = None, out: "torch.Tensor | None" = None,
+                  relu: bool = False) -> torch.Tensor:
     """``F.linear(x, weight, bias)`` for fp32 CUDA tensors on the tcgen05 tensor cores with fp32-grade accuracy.
 
     x (..., K) with a contiguous last dim (row pitch may exceed K); weight (N, K); returns (..., N).
     row_zero: optional bool/uint8 tensor with one entry per row of x: rows flagged non-zero come out as zeros.
+    relu: apply ``max(y, 0)`` in the GEMM epilogue (feed-forward ``activation(linear1(x))``); not with ``row_zero``.
     """
     if not x.is_cuda:
         raise RuntimeError("Not implemented on the CPU")
@@ -69,6 +71,14 @@ def linear_3xtf32(x: torch.Tensor, weight: torch.Tensor, bias: "torch.Tensor | N
         if rz.numel() != M:
             raise ValueError("row_zero must have one entry per row of x")
     b = bias.detach().contiguous() if bias is not None else None
+    if relu:
+        if rz is not None:
+            raise ValueError("linear_3xtf32: relu and row_zero cannot be combined")
+        _native.check(_native.lib().msda_b200_linear_relu_f32(
+            x2.data_ptr(), x2.stride(0), hi.data_ptr(), lo.data_ptr(), b.data_ptr() if b is not None else None,
+            M, N, K, y2.data_ptr(), y2.stride(0), torch.cuda.current_stream(x.device).cuda_stream),
+            "msda_b200_linear_relu_f32")
+        return out
     _native.check(_native.lib().msda_b200_linear_f32(
         x2.data_ptr(), x2.stride(0), hi.data_ptr(), lo.data_ptr(), b.data_ptr() if b is not None else None,
         rz.data_ptr() if rz is not None else None, M, N, K, y2.data_ptr(), y2.stride(0),

@@ -182,6 +182,10 @@ int msda_b200_backward_f32(const float* value, const int64_t* shapes, const int6
 int msda_b200_linear_split_weight_f32(const float* w, int N, int K, float* w_hi, float* w_lo, void* stream);
 int msda_b200_linear_f32(const float* x, int ldx, const float* w_hi, const float* w_lo, const float* bias,
                          const unsigned char* row_zero, int M, int N, int K, float* y, int ldy, void* stream);
+/* same GEMM with y = max(y, 0) in the epilogue: linear1 + ReLU of the encoder / decoder feed-forward block
+ * (third_party/adet/layers/deformable_transformer.py:248-252 forward_ffn, :406-411) */
+int msda_b200_linear_relu_f32(const float* x, int ldx, const float* w_hi, const float* w_lo, const float* bias,
+                              int M, int N, int K, float* y, int ldy, void* stream);
 /* diagnostics: per-CTA clock64 stamps of the following msda_b200_linear_f32 launches are written to buf
  * (device memory, [CTAs][8] int64: start, first stage full, split done, last MMA issued, accumulator ready,
  * epilogue done); NULL switches tracing off.  tools/gemm_trace.py. */

@@ -1,0 +1,93 @@
+"""Encoder-layer drop-in: state-dict compatibility on the CPU, parity against outputs of the
+reference's own DeformableTransformerEncoderLayer (tests/golden/make_golden_encoder_layer.py) on the GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "encoder_layer_cases.npz")
+CASES = ["mask_pos", "plain"]
+
+
+def load(name):
+    z = np.load(GOLD)
+    c = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+    sd = {k[3:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("sd/")}
+    return c, sd
+
+
+def build(c, sd):
+    from gomatching_b200 import DeformableTransformerEncoderLayer
+    d_model, d_ffn, heads, levels, points = [int(v) for v in c["cfg"]]
+    layer = DeformableTransformerEncoderLayer(d_model, d_ffn, 0.1, "relu", levels, heads, points).eval()
+    missing, unexpected = layer.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return layer
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_state_dict_of_the_reference_layer_loads_unchanged(name):
+    c, sd = load(name)
+    layer = build(c, sd)
+    assert sorted(layer.state_dict().keys()) == sorted(sd.keys())
+    for k, v in layer.state_dict().items():
+        assert v.shape == sd[k].shape, k
+
+
+def test_cpu_tensors_raise_like_the_reference_operator():
+    c, sd = load("plain")
+    layer = build(c, sd)
+    src = torch.from_numpy(c["src"])
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        layer(src, None, torch.from_numpy(c["ref"]), torch.from_numpy(c["shapes"]), torch.from_numpy(c["lsi"]), None)
+    # the feed-forward block alone is plain torch on the CPU (eager reference sequence)
+    out = layer.forward_ffn(src)
+    assert float((out - torch.from_numpy(c["ffn_only"])).abs().max()) <= 1e-5
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("tc", [True, False])
+def test_layer_matches_the_reference_layer_output(name, tc):
+    c, sd = load(name)
+    layer = build(c, sd).cuda()
+    layer.tensor_core_ffn = tc
+    layer.self_attn.tensor_core_projections = tc
+    src = torch.from_numpy(c["src"]).cuda()
+    pos = torch.from_numpy(c["pos"]).cuda() if c["pos"].size else None
+    mask = torch.from_numpy(c["mask"]).cuda() if c["mask"].size else None
+    ref, sh, lsi = torch.from_numpy(c["ref"]).cuda(), torch.from_numpy(c["shapes"]).cuda(), torch.from_numpy(c["lsi"]).cuda()
+    with torch.no_grad():
+        out = layer(src, pos, ref, sh, lsi, mask)
+        ffn = layer.forward_ffn(src)
+    assert rel(out.cpu(), torch.from_numpy(c["out"])) <= 1e-4           # the fp32 bar of the operator
+    assert rel(ffn.cpu(), torch.from_numpy(c["ffn_only"])) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_ffn_on_tensor_cores_is_fp32_grade_at_full_width():
+    """d_ffn = 1024 (the DeepSolo setting), 3 000 tokens: the 3xTF32 feed-forward block against float64."""
+    from gomatching_b200 import DeformableTransformerEncoderLayer
+    torch.manual_seed(3)
+    layer = DeformableTransformerEncoderLayer(256, 1024, 0.1, "relu", 4, 8, 4).cuda().eval()
+    src = torch.randn(2, 1500, 256, device="cuda")
+    with torch.no_grad():
+        got = layer.forward_ffn(src)
+        layer.tensor_core_ffn = False
+        eager = layer.forward_ffn(src)
+        l64 = DeformableTransformerEncoderLayer(256, 1024, 0.1, "relu", 4, 8, 4).double().cuda().eval()
+        l64.load_state_dict({k: v.double() for k, v in layer.state_dict().items()})
+        ref = l64.forward_ffn(src.double())
+    e_tc, e_eager = rel(got.double(), ref), rel(eager.double(), ref)
+    assert e_tc <= 2e-5, e_tc
+    assert e_tc <= 20 * max(e_eager, 1e-7)
+    # training mode with dropout keeps the eager path (and its randomness)
+    layer.tensor_core_ffn = True
+    layer.train()
+    assert not layer._ffn_on_tensor_cores(src)

@@ -69,4 +69,52 @@ for kind in ("encoder", "decoder"):
                  "frames": F, "Lq": Lq, "max_norm_diff_tc_vs_cublas": err}
     print("%s F=%d Lq=%d: module forward  tcgen05 3xTF32 %.1f us | cuBLAS fp32 + fused sampler %.1f us | reference structure "
           "(cuBLAS fp32, eager glue, core kernel) %.1f us | tc vs cuBLAS max-norm diff %.2e" % (kind, F, Lq, t_tc, t_cublas, t_eager, err))
+
+# ---- encoder layer (deformable_transformer.py:218-278): self-attention + residual/LayerNorm + feed-forward block ----
+torch.manual_seed(2)
+layer = g.DeformableTransformerEncoderLayer(256, 1024, 0.1, "relu", 4, 8, 4).to(dev).eval()
+with torch.no_grad():
+    layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+    layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+FL = min(F, 4)          # the 1024-wide hidden activation is 628 MB per frame
+ref = syn.encoder_reference_points(shapes_l, 1).expand(FL, -1, -1, -1).contiguous().to(dev)
+lsets = [(torch.randn(FL, S, 256, device=dev), torch.randn(FL, S, 256, device=dev) * 0.1) for _ in range(2)]
+
+
+def lrun(i):
+    src, pos = lsets[i % len(lsets)]
+    return layer(src, pos, ref, shapes, lsi, None)
+
+
+def ltime():
+    with torch.no_grad():
+        for i in range(2):
+            lrun(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(10):
+            lrun(i)
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 10 * 1e3
+
+
+layer.tensor_core_ffn = True
+layer.self_attn.tensor_core_projections, layer.self_attn.use_fused, layer.self_attn.merge_query_projections = True, True, True
+t_tc = ltime()
+with torch.no_grad():
+    o_tc = lrun(0).clone()
+layer.tensor_core_ffn = False
+layer.self_attn.tensor_core_projections = False
+t_cb = ltime()
+with torch.no_grad():
+    o_cb = lrun(0).clone()
+layer.self_attn.use_fused, layer.self_attn.merge_query_projections = False, False
+t_ref = ltime()
+err = float((o_tc - o_cb).abs().max() / o_cb.abs().max())
+res["encoder_layer"] = {"tcgen05_3xtf32_us": t_tc, "cublas_fp32_fused_sampler_us": t_cb, "reference_structure_us": t_ref,
+                        "frames": FL, "max_norm_diff_tc_vs_cublas": err}
+print("encoder LAYER F=%d (attention + LayerNorm + 256-1024-256 feed-forward): tcgen05 3xTF32 %.1f us | cuBLAS fp32 %.1f us | "
+      "reference structure %.1f us | tc vs cuBLAS max-norm diff %.2e" % (FL, t_tc, t_cb, t_ref, err))
 print(json.dumps(res))
