@@ -143,8 +143,9 @@ def staged_shape_hint(spatial_shapes, level_start_index) -> None:
     if hit is None:
         if len(_shape_hint_cache) > 64:
             _shape_hint_cache.clear()
-        sh = spatial_shapes.detach().to("cpu", copy=True).to(dtype=__import__("torch").int64).contiguous()
-        ls = level_start_index.detach().to("cpu", copy=True).to(dtype=__import__("torch").int64).contiguous()
+        import torch
+        sh = spatial_shapes.detach().to("cpu", copy=True).to(dtype=torch.int64).contiguous()
+        ls = level_start_index.detach().to("cpu", copy=True).to(dtype=torch.int64).contiguous()
         hit = _shape_hint_cache[key] = (sh, ls)
     sh, ls = hit
     lib().msda_b200_staged_set_host_shapes(sh.data_ptr(), ls.data_ptr(), int(ls.numel()))

@@ -41,6 +41,7 @@
 #include <mutex>
 #include <type_traits>
 #include "msda_fast_common.cuh"
+#include "tma_common.cuh"
 #include "msda_launch.h"
 #include <string.h>
 #include "../../include/msda_b200.h"
@@ -76,19 +77,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // ---- TMA window fill (used when the level shapes are known on the host: msda_b200_staged_set_host_shapes) ----
 struct StagedMaps { CUtensorMap lv[kSgL]; };
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nSG_WAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra SG_WAIT_DONE;\nbra SG_WAIT_LOOP;\nSG_WAIT_DONE:\n}\n" ::"r"(bar),
-      "r"(parity) : "memory");
-}
 // value viewed as (N, H_l, W_l, M, D): box = {D, 1 head, WW, WH, 1 frame}; out-of-map pixels arrive as zeros
 __device__ __forceinline__ void tma_window(uint32_t dst, const CUtensorMap* map, uint32_t bar, int m, int w0, int h0, int b) {
-  asm volatile("cp.async.bulk.tensor.5d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(0), "r"(m), "r"(w0), "r"(h0), "r"(b) : "memory");
+  tma_load_5d(dst, map, bar, 0, m, w0, h0, b);
 }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int OFF> __device__ __forceinline__ uint4 lds128_at(uint32_t a) {
@@ -123,7 +114,7 @@ __global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kern
   if (TMA && tid == 0) {
     mbar_init((uint32_t)__cvta_generic_to_shared(&sBar[0]), 1);
     mbar_init((uint32_t)__cvta_generic_to_shared(&sBar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
   const int QL = p.staged_levels;          // query levels served here (tiles of level ql: (8 >> ql) x (16 >> ql))
@@ -463,23 +454,6 @@ struct HostShapes { bool valid = false; long long hw[kSgL][2]; long long lsi[kSg
 HostShapes g_host_shapes;
 std::mutex g_host_shapes_mutex;
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn staged_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 // One 5-D map per sampled level over value (N, S, M, D) fp32: (D, M, W_l, H_l, N), base at the level's first pixel.
 bool make_window_maps(const FwdParams& p, StagedMaps& maps) {
   HostShapes hs;
@@ -487,7 +461,7 @@ bool make_window_maps(const FwdParams& p, StagedMaps& maps) {
     std::lock_guard<std::mutex> lock(g_host_shapes_mutex);
     hs = g_host_shapes;
   }
-  EncodeTiledFn fn = staged_encode_fn();
+  EncodeTiledFn fn = tensor_map_encode_fn();
   if (!hs.valid || !fn) return false;
   long long total = 0;
   for (int l = 0; l < kSgL; ++l) total += hs.hw[l][0] * hs.hw[l][1];
