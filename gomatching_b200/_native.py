@@ -38,6 +38,7 @@ SYMBOLS = (
     "msda_b200_forward_f32_host",
     "msda_b200_frames_u8_to_chw_f32",
     "msda_b200_staged_set_host_shapes",
+    "msda_b200_add_layernorm_f32",
 )
 
 
@@ -116,6 +117,8 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_linear_relu_f32.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, vp, ci, vp]
         L.msda_b200_linear_set_trace.restype = None
         L.msda_b200_linear_set_trace.argtypes = [vp]
+        L.msda_b200_add_layernorm_f32.restype = ci
+        L.msda_b200_add_layernorm_f32.argtypes = [vp, vp, vp, vp, ctypes.c_float, ctypes.c_longlong, ci, vp, vp]
         L.msda_b200_staged_set_host_shapes.restype = None
         L.msda_b200_staged_set_host_shapes.argtypes = [vp, vp, ci]
         L.msda_b200_frames_u8_to_chw_f32.restype = ci

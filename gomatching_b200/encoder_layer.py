@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .ms_deform_attn import MSDeformAttn
+from .norm import add_layernorm, add_layernorm_supported
 from .projections import linear_3xtf32
 
 
@@ -48,6 +49,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
         self.tensor_core_ffn = True
+        self.fused_add_norm = True     # inference: residual add + LayerNorm as one kernel (norm.add_layernorm)
 
     @staticmethod
     def with_pos_embed(tensor, pos):
@@ -69,16 +71,22 @@ class DeformableTransformerEncoderLayer(nn.Module):
             src2 = linear_3xtf32(hidden, self.linear2.weight, self.linear2.bias)
         else:
             src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
-        src = src + self.dropout3(src2)
-        src = self.norm2(src)
-        return src
+        return self._add_norm(src, src2, self.dropout3, self.norm2)
+
+    def _add_norm(self, src, src2, dropout, norm):
+        """``norm(src + dropout(src2))``; one kernel when nothing needs a gradient and dropout is inactive."""
+        needs_grad = torch.is_grad_enabled() and (src.requires_grad or src2.requires_grad or
+                                                  (norm.weight is not None and norm.weight.requires_grad))
+        if (self.fused_add_norm and not needs_grad and not (self.training and dropout.p > 0)
+                and add_layernorm_supported(src, norm)):
+            return add_layernorm(src, src2, norm)
+        return norm(src + dropout(src2))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         # self attention
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
                               padding_mask)
-        src = src + self.dropout1(src2)
-        src = self.norm1(src)
+        src = self._add_norm(src, src2, self.dropout1, self.norm1)
         # ffn
         src = self.forward_ffn(src)
         return src

@@ -213,6 +213,14 @@ int  msda_b200_forward_f32_host(msda_b200_host_ctx_t* ctx,
 int msda_b200_frames_u8_to_chw_f32(const unsigned char* frames, int N, int H, int W, int flip_channels,
                                    const float* mean3, const float* std3, int Hp, int Wp, float* out, void* stream);
 
+/* ---- residual add + LayerNorm in one pass: out = LayerNorm(x + y) * gamma + beta ------------------------------
+ * The two eager steps after every attention / feed-forward block of the transformer at inference
+ * (third_party/adet/layers/deformable_transformer.py:251-252, :272-273).  x, y (may be NULL), out: (rows, C) fp32
+ * contiguous; gamma, beta: (C) or NULL; biased variance, eps inside the square root, like nn.LayerNorm.
+ * C % 128 == 0, C <= 1024, 16-byte aligned pointers. */
+int msda_b200_add_layernorm_f32(const float* x, const float* y, const float* gamma, const float* beta, float eps,
+                                long long rows, int C, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

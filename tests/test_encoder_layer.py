@@ -91,3 +91,40 @@ def test_ffn_on_tensor_cores_is_fp32_grade_at_full_width():
     layer.tensor_core_ffn = True
     layer.train()
     assert not layer._ffn_on_tensor_cores(src)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,c,with_y,affine", [(19160, 256, True, True), (777, 128, True, True), (3, 1024, False, True),
+                                                 (4097, 384, True, False), (64, 256, True, True)])
+def test_add_layernorm_matches_torch(rows, c, with_y, affine):
+    """out = LayerNorm(x + y): against torch in float64 and against the eager fp32 ops (deformable_transformer.py:251-252)."""
+    from gomatching_b200.norm import add_layernorm
+    torch.manual_seed(rows + c)
+    norm = torch.nn.LayerNorm(c, elementwise_affine=affine).cuda()
+    if affine:
+        with torch.no_grad():
+            norm.weight.normal_(1.0, 0.2)
+            norm.bias.normal_(0.0, 0.2)
+    x = torch.randn(2, rows, c, device="cuda") * 3 + 0.5
+    y = torch.randn(2, rows, c, device="cuda") if with_y else None
+    with torch.no_grad():
+        got = add_layernorm(x, y, norm)
+        eager = norm(x + y if with_y else x)
+        n64 = torch.nn.LayerNorm(c, elementwise_affine=affine).double().cuda()
+        if affine:
+            n64.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+        ref = n64((x.double() + y.double()) if with_y else x.double())
+    assert got.shape == eager.shape and got.dtype == torch.float32
+    e_got, e_eager = rel(got.double(), ref), rel(eager.double(), ref)
+    assert e_got <= 2e-6, e_got
+    assert e_got <= 4 * max(e_eager, 1e-7)
+
+
+@pytest.mark.gpu
+def test_add_layernorm_fallbacks_and_cpu():
+    from gomatching_b200.norm import add_layernorm
+    norm = torch.nn.LayerNorm(100).cuda()                      # C not a multiple of 128: eager path, same result
+    x, y = torch.randn(5, 100, device="cuda"), torch.randn(5, 100, device="cuda")
+    assert torch.equal(add_layernorm(x, y, norm), norm(x + y))
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        add_layernorm(torch.randn(2, 256), None, torch.nn.LayerNorm(256))

@@ -100,12 +100,12 @@ def ltime():
     return e0.elapsed_time(e1) / 10 * 1e3
 
 
-layer.tensor_core_ffn = True
+layer.tensor_core_ffn = layer.fused_add_norm = True
 layer.self_attn.tensor_core_projections, layer.self_attn.use_fused, layer.self_attn.merge_query_projections = True, True, True
 t_tc = ltime()
 with torch.no_grad():
     o_tc = lrun(0).clone()
-layer.tensor_core_ffn = False
+layer.tensor_core_ffn = layer.fused_add_norm = False
 layer.self_attn.tensor_core_projections = False
 t_cb = ltime()
 with torch.no_grad():
