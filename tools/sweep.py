@@ -53,18 +53,23 @@ def main():
     ap.add_argument("--top", type=int, default=12)
     ap.add_argument("--staged-diag", action="store_true",
                     help="also time the staged kernel's diagnostic builds (variants 1-4: WRONG results, time attribution only)")
+    ap.add_argument("--height", type=int, default=720)
+    ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     F = args.frames
-    one = bench.algorithmic_bytes(F, 19160, 19160 if args.kind == "encoder" else 2500)
+    bench.HEIGHT, bench.WIDTH = args.height, args.width
+    from gomatching_b200 import synthetic as syn
+    S_all = sum(h * w for h, w in syn.level_shapes(args.height, args.width, 4))
+    one = bench.algorithmic_bytes(F, S_all, S_all if args.kind == "encoder" else 2500)
     nsets = max(2, int(4 * 126e6 / one) + 1)
     sets = [bench.device_workload(args.kind, F, 300 + i, args.dist, dev) for i in range(nsets)]
     for w in sets:
         w["loc"], w["attn"] = g.locations_softmax(w["shapes"], w["ref"], w["offsets"], w["logits"], 8)
         if args.dtype == "bf16":
             w["value"] = w["value"].to(torch.bfloat16)
-    b_alg = one if args.dtype == "f32" else one - F * 19160 * 256 * 2 - F * sets[0]["Lq"] * 256 * 2
+    b_alg = one if args.dtype == "f32" else one - F * S_all * 256 * 2 - F * sets[0]["Lq"] * 256 * 2
 
     def runner(tn):
         if args.fused:
@@ -99,7 +104,7 @@ def main():
         results.append({"tuning": tn, "us": us, "gbs": b_alg / us / 1e3})
     results.sort(key=lambda r: r["us"])
     base = time_launches(runner(None), sets, args.iters)
-    print("== %s frames=%d dtype=%s fused=%d dist=%s  B_alg=%.2f MB  sets=%d" % (args.kind, F, args.dtype, args.fused,
+    print("== %s %dx%d frames=%d dtype=%s fused=%d dist=%s  B_alg=%.2f MB  sets=%d" % (args.kind, args.height, args.width, F, args.dtype, args.fused,
                                                                                args.dist, b_alg / 1e6, nsets))
     print("default heuristics: %.2f us  %.0f GB/s" % (base, b_alg / base / 1e3))
     for r in results[:args.top]:
