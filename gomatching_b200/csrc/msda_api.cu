@@ -51,7 +51,9 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
   // operator in encoder self-attention; everything else runs linear query tiles
   if (mode == 0) mode = !can_tile ? kModeGeneric : ((self_attn && elem_bytes == 4 && !fused) ? kModePyramid : kModeLinear);
   if (mode == kModePyramid && !self_attn) mode = kModeLinear;
-  if (mode == kModeStaged && !(self_attn && elem_bytes == 4 && can_tile && fast_shape_supported(p.D, p.L, p.P))) mode = kModeLinear;
+  if ((mode == kModeStaged || mode == kModePipelined) &&
+      !(self_attn && elem_bytes == 4 && can_tile && fast_shape_supported(p.D, p.L, p.P)))
+    mode = kModeLinear;
   if (mode != kModeGeneric && !can_tile) {
     if (fused) return MSDA_E_UNSUPPORTED;
     mode = kModeGeneric;
@@ -66,6 +68,14 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
   int tw = (tn && tn->tile_w > 0) ? tn->tile_w : 8;
   int tq = (tn && tn->tile_q > 0) ? tn->tile_q : ((self_attn && elem_bytes == 2) ? 256 : 64);
   int cps = (tn && tn->ctas_per_sm > 0) ? tn->ctas_per_sm : (mode == kModePyramid ? 3 : 4);
+  if (mode == kModePipelined) {
+    // producer / consumer window kernel for the level-0 queries (one CTA per SM = grid / 4), 64-query linear tiles for the rest
+    p.staged_levels = 1;
+    p.tile_q = tq;
+    p.tile_h = 0; p.tile_w_log2 = 0;
+    p.grid = sms * 4;
+    return 0;
+  }
   if (mode == kModeStaged) {
     // staged kernel: two 256-thread CTAs per SM; the remaining query levels run 64-query linear tiles (variant 3)
     p.staged_levels = (tn && tn->tile_h > 0 && tn->tile_h <= 3) ? tn->tile_h : 1;

@@ -452,6 +452,26 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
     return (int)cudaGetLastError();
   }
   const int LP = p.L * p.P;
+  if (p.mode == kModePipelined) {
+    long long hw[4][2], lsi[4];
+    if (sizeof(T) == 4 && staged_supported(p) && staged_get_host_shapes(hw, lsi)) {
+      FwdParams lv0 = p;
+      lv0.grid = p.grid / 4;                              // one 17-warp CTA per SM
+      const int rc = launch_forward_pipelined_f32(lv0, hw, lsi, stream);
+      if (rc != MSDA_E_UNSUPPORTED) {
+        if (rc) return rc;
+        FwdParams rest = p;                               // query levels 1..3: register-gather kernel
+        rest.mode = kModeLinear;
+        rest.q_level_begin = 1;
+        rest.variant = 3;
+        return launch_forward_fast_f32(rest, stream);
+      }
+    }
+    FwdParams all = p;                                    // no host geometry: everything on the register-gather kernel
+    all.mode = kModeLinear;
+    all.variant = 3;
+    return sizeof(T) == 4 ? launch_forward_fast_f32(all, stream) : launch_forward_fast_bf16(all, stream);
+  }
   if (p.mode == kModeStaged) {
     if (sizeof(T) != 4 || !staged_supported(p)) return MSDA_E_UNSUPPORTED;
     int rc = launch_forward_staged_f32(p, stream);      // queries of pyramid levels 0 .. staged_levels-1

@@ -1,0 +1,381 @@
+// Pipelined shared-memory-window kernel for fp32 encoder self-attention (Lq == S, D = 32, L = 4, P = 4): the staged
+// kernel of msda_forward_staged.cu re-cut as a producer / consumer pipeline without any CTA-wide barrier.
+//
+// What the staged kernel measured (profiles/r01_s21_*, r01_s22_*): its gather passes run at the L1 pipe's limit and TMA
+// window fills hide, but the per-item front end (phase 1, window placement by a CTA-wide mean, six __syncthreads) does
+// not overlap with anything: 133 us of 390.  Here
+//   * one CTA per SM: 16 consumer warps + 1 producer warp.  A work item is (frame, head, 8 x 16 tile of level-0 queries);
+//     a CTA owns a CONTIGUOUS range of items (same head, raster-adjacent tiles);
+//   * four window slots in shared memory, one per sampled level (20x28, 16x20, 14x16, 13x14 pixels of 128-byte rows),
+//     each with a `full` mbarrier (TMA transaction bytes) and an `empty` mbarrier (one arrival per consumer warp).  The
+//     producer refills slot l for item n+1 as soon as every consumer warp has finished pass l of item n -- three passes
+//     ahead of its next use;
+//   * a consumer warp owns 8 units of the tile and runs on its own: phase 1 -> records {h_low|w_low, lh, lw, attention}
+//     in its private shared-memory strip -> for each level: wait full, turn h_low / w_low into window offsets, gather
+//     with LDS.128, arrive on empty.  Samples outside the window take predicated global loads (same arithmetic);
+//   * window placement: the tile's geometric image in the sampled level plus the offset the PREVIOUS item of the same
+//     head measured between its samples' mean and its own geometric centre (the heads' directional bias), published by
+//     the consumers with shared atomics during their phase 1 and read by the producer after the `empty` barrier of
+//     level 0 -- so the producer never waits for data of the item it is fetching.
+// Results are bit-identical to every other kernel: level-major accumulation order, the reference's FMUL/FFMA chain in
+// packed fp32x2, zero padding by the TMA unit's out-of-bounds fill, and window placement only decides which of two
+// equivalent load paths a sample takes.  Needs the level geometry on the host (msda_b200_staged_set_host_shapes).
+#include <mutex>
+#include <type_traits>
+#include <string.h>
+#include "msda_fast_common.cuh"
+#include "tma_common.cuh"
+#include "msda_launch.h"
+#include "../../include/msda_b200.h"
+
+namespace msda {
+
+namespace {
+
+constexpr int kPlCons = 16;                              // consumer warps
+constexpr int kPlThreads = (kPlCons + 1) * 32;           // + 1 producer warp
+constexpr int kPlUPW = 8;                                // units per consumer warp: 128 units per tile
+constexpr int kPlTH = 8, kPlTWlog2 = 4;                  // 8 x 16 level-0 queries
+constexpr int kPlL = 4, kPlP = 4, kPlLPT = 16;
+constexpr int kPlRowB = 128;
+
+__host__ __device__ constexpr int pl_wh(int l) { return l == 0 ? 20 : l == 1 ? 16 : l == 2 ? 14 : 13; }
+__host__ __device__ constexpr int pl_ww(int l) { return l == 0 ? 28 : l == 1 ? 20 : l == 2 ? 16 : 14; }
+__host__ __device__ constexpr int pl_rows(int l) { return pl_wh(l) * pl_ww(l); }
+__host__ __device__ constexpr int pl_woff(int l) { return l == 0 ? 0 : pl_woff(l - 1) + pl_rows(l - 1) * kPlRowB; }
+constexpr int kPlRecBytes = kPlCons * kPlLPT * kPlUPW * 16;             // 32 KB
+constexpr int kPlWinBytes = pl_woff(3) + pl_rows(3) * kPlRowB;          // 164608 B
+constexpr int kPlSmem = kPlRecBytes + kPlWinBytes;
+
+struct PipeGeom {
+  CUtensorMap lv[kPlL];
+  int H[kPlL], W[kPlL], start[kPlL];
+};
+
+template <int OFF> __device__ __forceinline__ uint4 pl_lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a), "n"(OFF));
+  return r;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const FwdParams p, const __grid_constant__ PipeGeom geo) {
+  constexpr int NL = kPlL, PT = kPlP, LPT = kPlLPT, SPL = 4, D = 32;
+  extern __shared__ __align__(128) unsigned char pl_smem[];
+  __shared__ __align__(8) unsigned long long sFull[NL], sEmpty[NL];
+  __shared__ int sSum[2][NL][4];      // per item parity, per sampled level: sum h_low, sum w_low, count
+  __shared__ int sOrg[2][NL][2];      // per item parity, per sampled level: window origin (h0, w0) chosen by the producer
+
+  const int M = p.M, Lq = p.Lq;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 2 * NL * 4) (&sSum[0][0][0])[tid] = 0;
+  if (tid == 0) {
+    for (int l = 0; l < NL; ++l) {
+      mbar_init(smem_u32(&sFull[l]), 1);
+      mbar_init(smem_u32(&sEmpty[l]), kPlCons);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const uint32_t sWinBase = smem_u32(pl_smem + kPlRecBytes);
+  const int cstride = M * kPlRowB;
+  const int ntx = (geo.W[0] + (1 << kPlTWlog2) - 1) >> kPlTWlog2, nty = (geo.H[0] + kPlTH - 1) / kPlTH;
+  const int tiles = ntx * nty;
+  const int total = p.N * M * tiles;                       // item = (b * M + m) * tiles + tile
+  const int per_cta = (total + gridDim.x - 1) / gridDim.x;
+  const int first = blockIdx.x * per_cta;
+  const int count = max(0, min(per_cta, total - first));
+
+  // geometric image of tile (ty, tx) in sampled level l: top-left window corner that centres the image
+  auto geo_origin = [&](int l, int ty, int tx, int& gh, int& gw) {
+    const float sy = (float)geo.H[l] / (float)geo.H[0], sx = (float)geo.W[l] / (float)geo.W[0];
+    const float cy = ((float)(ty * kPlTH) + 0.5f * (float)kPlTH) * sy - 0.5f;      // image of the tile centre
+    const float cx = ((float)(tx << kPlTWlog2) + 0.5f * (float)(1 << kPlTWlog2)) * sx - 0.5f;
+    gh = __float2int_rd(cy) - (pl_wh(l) - 2) / 2;
+    gw = __float2int_rd(cx) - (pl_ww(l) - 2) / 2;
+  };
+
+  if (warp == kPlCons) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      int prev_m = -1, prev_gh[NL], prev_gw[NL], prev_h0[NL], prev_w0[NL];
+      for (int n = 0; n < count; ++n) {
+        const int item = first + n;
+        const int tile = item % tiles, bm = item / tiles;
+        const int m = bm % M, b = bm / M;
+        const int ty = tile / ntx, tx = tile - ty * ntx;
+        const uint32_t prev_par = (uint32_t)(n - 1) & 1u;
+        if (n >= 1) mbar_wait(smem_u32(&sEmpty[0]), prev_par);        // pass 0 of item n-1 is over: its phase-1 sums are complete
+        int h0[NL], w0[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          int gh, gw;
+          geo_origin(l, ty, tx, gh, gw);
+          int dh = 0, dw = 0;
+          if (n >= 1 && m == prev_m) {
+            const int cnt = sSum[(n - 1) & 1][l][2];
+            if (cnt > 0) {     // where item n-1 would have wanted its window, relative to its geometric origin
+              const float inv = 1.0f / (float)cnt;
+              dh = __float2int_rn((float)sSum[(n - 1) & 1][l][0] * inv) - (pl_wh(l) - 2) / 2 - prev_gh[l];
+              dw = __float2int_rn((float)sSum[(n - 1) & 1][l][1] * inv) - (pl_ww(l) - 2) / 2 - prev_gw[l];
+            } else {
+              dh = prev_h0[l] - prev_gh[l];
+              dw = prev_w0[l] - prev_gw[l];
+            }
+          }
+          prev_gh[l] = gh; prev_gw[l] = gw;
+          int ch = gh + dh, cw = gw + dw;
+          ch = min(ch, geo.H[l] + 1 - pl_wh(l));
+          cw = min(cw, geo.W[l] + 1 - pl_ww(l));
+          h0[l] = max(ch, -1);
+          w0[l] = max(cw, -1);
+          prev_h0[l] = h0[l]; prev_w0[l] = w0[l];
+          sOrg[n & 1][l][0] = h0[l];
+          sOrg[n & 1][l][1] = w0[l];
+        }
+        if (n >= 1) {
+#pragma unroll
+          for (int l = 0; l < NL; ++l) { sSum[(n - 1) & 1][l][0] = 0; sSum[(n - 1) & 1][l][1] = 0; sSum[(n - 1) & 1][l][2] = 0; }
+        }
+        prev_m = m;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          if (n >= 1 && l >= 1) mbar_wait(smem_u32(&sEmpty[l]), prev_par);
+          const uint32_t bar = smem_u32(&sFull[l]);
+          mbar_expect_tx(bar, pl_rows(l) * kPlRowB);      // release: the origins above are visible to whoever sees the phase complete
+          tma_load_5d(sWinBase + pl_woff(l), &geo.lv[l], bar, 0, m, w0[l], h0[l], b);
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================== consumers ==============================
+  const int g = lane >> 2, k = lane & 3;                 // unit slot in the warp; lane in the unit = sampled level of its 4 samples
+  float4* sRec = reinterpret_cast<float4*>(pl_smem) + (size_t)warp * LPT * kPlUPW;
+  const float inv_p = 1.0f / (float)PT;
+  const int c0 = k * 16 + (g & 1) * 64;                  // first 16-byte chunk of a row this lane owns; the second is c0 +- 64
+  const int dhi = (g & 1) ? -64 : 64;
+  const int Hk = geo.H[k], Wk = geo.W[k];
+  const float Hf = (float)Hk, Wf = (float)Wk;
+
+  auto locate = [&](int item, bool& valid, size_t& bq, int& m, int& b) {
+    const int tile = item % tiles, bm = item / tiles;
+    m = bm % M; b = bm / M;
+    const int ty = tile / ntx, tx = tile - ty * ntx;
+    const int j = warp * kPlUPW + g;
+    const int y = ty * kPlTH + (j >> kPlTWlog2), x = (tx << kPlTWlog2) + (j & ((1 << kPlTWlog2) - 1));
+    valid = (y < geo.H[0]) && (x < geo.W[0]);
+    bq = (size_t)b * Lq + (valid ? geo.start[0] + y * geo.W[0] + x : 0);
+  };
+  auto prefetch = [&](Prefetched<SPL, 1, FUSED>& pf, size_t bq, int m) {
+    if constexpr (FUSED) {
+      ld_stream_vec<SPL>(p.logits + bq * p.logit_pitch + m * LPT + k * SPL, pf.lg);
+      ld_stream_vec<2 * SPL>(p.offsets + bq * p.off_pitch + (m * LPT + k * SPL) * 2, pf.off);
+      const float* rp = p.ref + (bq * NL + k) * p.ref_dim;
+      if (p.ref_dim == 4) {
+        pf.ref[0] = __ldg(reinterpret_cast<const float4*>(rp));
+      } else {
+        const float2 r2 = __ldg(reinterpret_cast<const float2*>(rp));
+        pf.ref[0] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
+      }
+    } else {
+      const size_t unit = bq * M + m;
+      ld_stream_vec<2 * SPL>(p.loc + (unit * LPT + k * SPL) * 2, pf.xy);
+      ld_stream_vec<SPL>(p.attn + unit * LPT + k * SPL, pf.a);
+    }
+  };
+
+  bool n_valid = false;
+  size_t n_bq = 0;
+  int n_m = 0, n_b = 0;
+  Prefetched<SPL, 1, FUSED> pf;
+  if (count > 0) {
+    locate(first, n_valid, n_bq, n_m, n_b);
+    prefetch(pf, n_bq, n_m);
+  }
+
+  for (int n = 0; n < count; ++n) {
+    const bool valid = n_valid;
+    const int m = n_m, b = n_b;
+    const size_t unit = n_bq * M + m;
+    const uint32_t par = (uint32_t)n & 1u;
+    const char* vhead = reinterpret_cast<const char*>(p.value) + ((size_t)b * p.S * M + m) * kPlRowB;
+
+    // ---------------- phase 1: this lane's 4 samples (all of sampled level k) ----------------
+    {
+      float a[SPL], lx[SPL], ly[SPL];
+      if constexpr (FUSED) {
+        float mx = pf.lg[0];
+#pragma unroll
+        for (int i = 1; i < SPL; ++i) mx = fmaxf(mx, pf.lg[i]);
+#pragma unroll
+        for (int off = 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float v[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) { a[i] = expf(__fsub_rn(pf.lg[i], mx)); v[i] = a[i]; }
+#pragma unroll
+        for (int o = LPT / 2; o >= 1; o >>= 1) {
+          if (o >= SPL) {
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], o / SPL));
+          } else {
+            float t[SPL];
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) t[i] = __fadd_rn(v[i], v[i ^ o]);
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) v[i] = t[i];
+          }
+        }
+        const float sum = v[0];
+        const float4 rf = pf.ref[0];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          a[i] = __fdiv_rn(a[i], sum);
+          lx[i] = location_from_offset(rf.x, rf.z, pf.off[2 * i], Wf, inv_p, p.ref_dim);
+          ly[i] = location_from_offset(rf.y, rf.w, pf.off[2 * i + 1], Hf, inv_p, p.ref_dim);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) { lx[i] = pf.xy[2 * i]; ly[i] = pf.xy[2 * i + 1]; a[i] = pf.a[i]; }
+      }
+      int sh = 0, sw = 0, cnt = 0;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        // cuh:285-288 (one FFMA each), cuh:39-45
+        const float h_im = __fmaf_rn(ly[i], Hf, -0.5f);
+        const float w_im = __fmaf_rn(lx[i], Wf, -0.5f);
+        const bool inr = valid && (h_im > -1.0f) && (w_im > -1.0f) && (h_im < Hf) && (w_im < Wf);
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int hl = inr ? (int)hf : 0, wl = inr ? (int)wf : 0;
+        if (inr) { sh += hl; sw += wl; ++cnt; }
+        // h_low, w_low >= -1: stored + 1 in 16 bits each; 0xffffffff marks a skipped sample (cuh:288)
+        const uint32_t hw = inr ? (((uint32_t)(hl + 1) << 16) | (uint32_t)(wl + 1)) : 0xffffffffu;
+        sRec[(k * SPL + i) * kPlUPW + (g ^ (2 * k))] =
+            make_float4(__uint_as_float(hw), __fsub_rn(h_im, hf), __fsub_rn(w_im, wf), inr ? a[i] : 0.0f);
+      }
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {
+        sh += __shfl_xor_sync(0xffffffffu, sh, o);
+        sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+      if (g == 0 && cnt > 0) {
+        atomicAdd(&sSum[par][k][0], sh);
+        atomicAdd(&sSum[par][k][1], sw);
+        atomicAdd(&sSum[par][k][2], cnt);
+      }
+    }
+    __syncwarp();
+
+    // ---------------- next item: operand prefetch ----------------
+    if (n + 1 < count) {
+      locate(first + n + 1, n_valid, n_bq, n_m, n_b);
+      prefetch(pf, n_bq, n_m);
+    }
+
+    // ---------------- four level passes ----------------
+    f32x2 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = 0ull;
+    auto level_pass = [&](auto level_c) {
+      constexpr int l = decltype(level_c)::value;
+      mbar_wait(smem_u32(&sFull[l]), par);
+      const int h0 = sOrg[par][l][0], w0 = sOrg[par][l][1];
+      const uint32_t wbase = sWinBase + pl_woff(l) + c0;
+      const int Hl = geo.H[l], Wl = geo.W[l];
+#pragma unroll
+      for (int pt = 0; pt < PT; ++pt) {
+        const int s = l * PT + pt;
+        const float4 r = sRec[s * kPlUPW + (g ^ (2 * l))];
+        const uint32_t hw = __float_as_uint(r.x);
+        const int hl = (int)(hw >> 16) - 1, wl = (int)(hw & 0xffffu) - 1;
+        const int dh = hl - h0, dw = wl - w0;
+        const bool skipped = hw == 0xffffffffu;
+        const bool inwin = ((unsigned)dh <= (unsigned)(pl_wh(l) - 2)) && ((unsigned)dw <= (unsigned)(pl_ww(l) - 2));
+        RowVec<32> q[4];
+        if (inwin || skipped) {
+          // a skipped sample (attention 0) reads the window's first pixel: finite data, no effect on the sum
+          const uint32_t a0 = wbase + (skipped ? 0u : (uint32_t)((dh * pl_ww(l) + dw) * kPlRowB)), a1 = a0 + (uint32_t)dhi;
+          q[0].lo = pl_lds128<0>(a0);                              q[0].hi = pl_lds128<0>(a1);
+          q[1].lo = pl_lds128<kPlRowB>(a0);                        q[1].hi = pl_lds128<kPlRowB>(a1);
+          q[2].lo = pl_lds128<pl_ww(l) * kPlRowB>(a0);             q[2].hi = pl_lds128<pl_ww(l) * kPlRowB>(a1);
+          q[3].lo = pl_lds128<pl_ww(l) * kPlRowB + kPlRowB>(a0);   q[3].hi = pl_lds128<pl_ww(l) * kPlRowB + kPlRowB>(a1);
+        } else {
+          // footprint outside the window: predicated global loads, skipped corners read as zero (cuh:56-78)
+          const bool top = hl >= 0, bot = hl + 1 <= Hl - 1, lef = wl >= 0, rig = wl + 1 <= Wl - 1;
+          const char* c1 = vhead + (ptrdiff_t)((geo.start[l] + hl * Wl + wl) * cstride) + c0;
+          const char* c3 = c1 + Wl * cstride;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) q[c].zero();
+          if (top && lef) { q[0].lo = ld_value16(c1);            q[0].hi = ld_value16(c1 + dhi); }
+          if (top && rig) { q[1].lo = ld_value16(c1 + cstride);  q[1].hi = ld_value16(c1 + cstride + dhi); }
+          if (bot && lef) { q[2].lo = ld_value16(c3);            q[2].hi = ld_value16(c3 + dhi); }
+          if (bot && rig) { q[3].lo = ld_value16(c3 + cstride);  q[3].hi = ld_value16(c3 + cstride + dhi); }
+        }
+        float w1, w2, w3, w4;
+        bilinear_weights(r.y, r.z, w1, w2, w3, w4);
+        accumulate_sample<float, 32, 4>(acc, make_float4(w1, w2, w3, w4), r.w, q[0], q[1], q[2], q[3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sEmpty[l]));      // this warp is done with slot l for this item
+    };
+    level_pass(std::integral_constant<int, 0>{});
+    level_pass(std::integral_constant<int, 1>{});
+    level_pass(std::integral_constant<int, 2>{});
+    level_pass(std::integral_constant<int, 3>{});
+    if (valid) {
+      char* op = reinterpret_cast<char*>(p.out) + unit * (size_t)(D * 4);
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) upk(acc[j], f[2 * j], f[2 * j + 1]);
+      st_stream16(op + c0, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+      st_stream16(op + c0 + dhi, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+    }
+    __syncwarp();   // the record strip is rewritten by the next item's phase 1
+  }
+}
+
+template <bool FUSED>
+int launch_pipelined(const FwdParams& p, const PipeGeom& geo, cudaStream_t stream) {
+  auto kern = msda_fwd_pipelined_kernel<FUSED>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  kern<<<p.grid, kPlThreads, kPlSmem, stream>>>(p, geo);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// Returns MSDA_E_UNSUPPORTED when the host-side level geometry is missing or does not match (the caller then uses
+// another kernel).  Serves the level-0 queries only; the caller runs the remaining levels on the register-gather kernel.
+int launch_forward_pipelined_f32(const FwdParams& p, const long long (*hw)[2], const long long* lsi, cudaStream_t stream) {
+  EncodeTiledFn fn = tensor_map_encode_fn();
+  if (!fn || !hw || !lsi) return MSDA_E_UNSUPPORTED;
+  PipeGeom geo;
+  memset(&geo, 0, sizeof(geo));
+  long long total = 0;
+  for (int l = 0; l < kPlL; ++l) total += hw[l][0] * hw[l][1];
+  if (total != p.S || hw[0][0] >= 32768 || hw[0][1] >= 32768) return MSDA_E_UNSUPPORTED;
+  const cuuint64_t row = (cuuint64_t)p.D * 4, px = (cuuint64_t)p.M * row;
+  for (int l = 0; l < kPlL; ++l) {
+    const cuuint64_t H = (cuuint64_t)hw[l][0], W = (cuuint64_t)hw[l][1];
+    geo.H[l] = (int)H; geo.W[l] = (int)W; geo.start[l] = (int)lsi[l];
+    cuuint64_t gdim[5] = {(cuuint64_t)p.D, (cuuint64_t)p.M, W, H, (cuuint64_t)p.N};
+    cuuint64_t gstride[4] = {row, px, W * px, (cuuint64_t)p.S * px};
+    cuuint32_t box[5] = {(cuuint32_t)p.D, 1, (cuuint32_t)pl_ww(l), (cuuint32_t)pl_wh(l), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = const_cast<char*>(reinterpret_cast<const char*>(p.value) + (size_t)lsi[l] * px);
+    if (fn(&geo.lv[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MSDA_E_UNSUPPORTED;
+  }
+  return p.loc == nullptr ? launch_pipelined<true>(p, geo, stream) : launch_pipelined<false>(p, geo, stream);
+}
+
+}  // namespace msda

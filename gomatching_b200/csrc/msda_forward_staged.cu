@@ -522,6 +522,17 @@ void staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host,
   g_host_shapes.valid = true;
 }
 
+bool staged_get_host_shapes(long long (*hw)[2], long long* lsi) {
+  std::lock_guard<std::mutex> lock(g_host_shapes_mutex);
+  if (!g_host_shapes.valid) return false;
+  for (int l = 0; l < kSgL; ++l) {
+    hw[l][0] = g_host_shapes.hw[l][0];
+    hw[l][1] = g_host_shapes.hw[l][1];
+    lsi[l] = g_host_shapes.lsi[l];
+  }
+  return true;
+}
+
 int launch_forward_staged_f32(const FwdParams& p, cudaStream_t stream) {
   if (p.loc != nullptr) {   // diagnostic variants (wrong results) exist for the core operator only
     if (p.variant == 1) return launch_staged<false, 1>(p, stream);    // no fallback path

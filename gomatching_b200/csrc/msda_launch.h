@@ -5,7 +5,7 @@
 
 namespace msda {
 
-enum TileMode { kModeLinear = 1, kModePyramid = 2, kModeGeneric = 3, kModeStaged = 4 };
+enum TileMode { kModeLinear = 1, kModePyramid = 2, kModeGeneric = 3, kModeStaged = 4, kModePipelined = 5 };
 
 struct FwdParams {
   const void* value;          // (N,S,M,D) fp32 or bf16
@@ -52,6 +52,10 @@ bool staged_supported(const FwdParams& p);
 int launch_forward_staged_f32(const FwdParams& p, cudaStream_t stream);
 // optional: level shapes on the host let the staged kernel fill its windows with TMA (tensor maps need them)
 void staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host, int L);
+bool staged_get_host_shapes(long long (*hw)[2], long long* lsi);   // 4 levels; false if no hint is set
+// producer / consumer version of the staged kernel (msda_forward_pipelined.cu): level-0 queries only, needs the hint;
+// MSDA_E_UNSUPPORTED if it cannot run (the caller falls back)
+int launch_forward_pipelined_f32(const FwdParams& p, const long long (*hw)[2], const long long* lsi, cudaStream_t stream);
 // true if the tiled kernels can run this problem (else only the generic kernel can)
 bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused);
 

@@ -80,7 +80,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     loc = sampling_loc if sampling_loc.dtype == torch.float32 else sampling_loc.float()
     attn = attn_weight if attn_weight.dtype == torch.float32 else attn_weight.float()
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-    if _native.tuning_mode(tuning) == 4:
+    if _native.tuning_mode(tuning) in (4, 5):
         _native.staged_shape_hint(spatial_shapes, level_start_index)
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream
@@ -143,7 +143,7 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
         raise RuntimeError("msda_b200: value dtype %s has no kernel" % value.dtype)
     f32 = value.dtype == torch.float32
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-    if _native.tuning_mode(tuning) == 4:
+    if _native.tuning_mode(tuning) in (4, 5):
         _native.staged_shape_hint(spatial_shapes, level_start_index)
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream

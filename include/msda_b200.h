@@ -61,7 +61,9 @@ extern "C" {
 typedef struct msda_b200_tuning {
   int32_t mode;          /* 0 auto | 1 linear query tiles | 2 pyramid 2-D tiles (needs Lq == S) | 3 generic kernel |
                             4 staged: value windows in shared memory (fp32 encoder self-attention, D=32 L=4 P=4);
-                            tile_h then = number of query levels staged (default 1), the rest runs mode 1 */
+                            tile_h then = number of query levels staged (default 1), the rest runs mode 1 |
+                            5 pipelined: producer / consumer version of 4 (TMA fills, no CTA-wide barriers); needs
+                            msda_b200_staged_set_host_shapes, else runs mode 1 */
   int32_t tile_h;        /* pyramid tile height in pixels (0 = default)                            */
   int32_t tile_w;        /* pyramid tile width in pixels, multiple of 4 (0 = default)              */
   int32_t tile_q;        /* linear tile length in queries (0 = default)                            */

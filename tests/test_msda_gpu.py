@@ -122,7 +122,7 @@ def test_setC_default_init_network_capture(setc_cases, tag):
     if tag == "enc0":      # Lq == S: the pyramid tiling is the default; force the others too
         for tuning in (dict(mode=1), dict(mode=2, tile_h=4, tile_w=4), dict(mode=2, tile_h=16, tile_w=16), dict(mode=3),
                        dict(mode=2, force_v1=1), dict(mode=2, variant=3), dict(mode=2, variant=5, tile_h=2, tile_w=32),
-                       dict(mode=4), dict(mode=4, tile_h=2), dict(mode=4, tile_h=3)):
+                       dict(mode=4), dict(mode=4, tile_h=2), dict(mode=4, tile_h=3), dict(mode=5)):
             assert np.array_equal(run_core(c, tuning).cpu().numpy(), out), tuning
 
 
@@ -160,7 +160,7 @@ def test_full_size_720p_bit_exact(kind, dist, n):
     ora = O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"])
     assert np.array_equal(out.cpu().numpy(), ora)
     if kind == "encoder":   # staged shared-memory-window kernel (windows + global fallback): same bits
-        for tuning in (dict(mode=4), dict(mode=4, tile_h=2)):
+        for tuning in (dict(mode=4), dict(mode=4, tile_h=2), dict(mode=5)):
             assert np.array_equal(run_core(c, tuning).cpu().numpy(), ora), tuning
             fz = g.ms_deform_attn_forward_fused(dev(w.value), dev(w.shapes), dev(w.lsi), dev(w.ref), dev(w.offsets),
                                                 dev(w.logits), tuning=tuning)
@@ -229,8 +229,7 @@ def test_staged_window_kernel_is_bit_identical(hw, n, dist):
     fbase = g.ms_deform_attn_forward_fused(v, sh, ls, rf, off, lg, tuning=dict(mode=1))
     box = torch.cat([rf, torch.full_like(rf, 0.05)], -1).contiguous()             # (N, Lq, L, 4): centre + (w, h)
     bbase = g.ms_deform_attn_forward_fused(v, sh, ls, box, off, lg, tuning=dict(mode=1))
-    for levels in (1, 2, 3):
-        tn = dict(mode=4, tile_h=levels)
+    for tn in (dict(mode=4, tile_h=1), dict(mode=4, tile_h=2), dict(mode=4, tile_h=3), dict(mode=5)):
         assert torch.equal(g.ms_deform_attn_forward(v, sh, ls, loc, at, 64, tuning=tn), base), tn
         assert torch.equal(g.ms_deform_attn_forward_fused(v, sh, ls, rf, off, lg, tuning=tn), fbase), tn
         assert torch.equal(g.ms_deform_attn_forward_fused(v, sh, ls, box, off, lg, tuning=tn), bbase), tn

@@ -92,7 +92,8 @@ def main():
     tiles += [dict(mode=1, tile_q=q) for q in ((64, 128, 256) if args.quick else (16, 32, 64, 128, 256))]
     staged = []
     if args.kind == "encoder" and args.dtype == "f32":   # shared-memory-window kernel: tile_h = query levels staged
-        staged = [dict(mode=4, tile_h=n, variant=v, ctas_per_sm=1, force_v1=0, walk=args.walk) for n in (1, 2, 3) for v in ((0, 1, 2, 3, 4) if n == 1 and not args.fused and args.staged_diag else (0,))]   # variant 1: diagnostic, no fallback path (wrong results)
+        staged = [dict(mode=4, tile_h=n, variant=v, ctas_per_sm=1, force_v1=0, walk=args.walk) for n in (1, 2, 3) for v in ((0, 1, 2, 3, 4) if n == 1 and not args.fused and args.staged_diag else (0,))]
+        staged.append(dict(mode=5, variant=0, ctas_per_sm=1, force_v1=0, walk=0))   # producer / consumer window kernel   # variant 1: diagnostic, no fallback path (wrong results)
     combos = [dict(t, variant=v, ctas_per_sm=cps, force_v1=args.force_v1, walk=args.walk)
               for v, t, cps in itertools.product(variants, tiles, cps_list)] + staged
     for tn in combos:
