@@ -4,19 +4,21 @@
 // What the staged kernel measured (profiles/r01_s21_*, r01_s22_*): its gather passes run at the L1 pipe's limit and TMA
 // window fills hide, but the per-item front end (phase 1, window placement by a CTA-wide mean, six __syncthreads) does
 // not overlap with anything: 133 us of 390.  Here
-//   * one CTA per SM: 16 consumer warps + 1 producer warp.  A work item is (frame, head, 8 x 16 tile of level-0 queries);
+//   * one CTA per SM: 16 consumer (gather) warps + 4 front-end (phase 1) warps + 1 producer warp.  A work item is (frame, head, 8 x 16 tile of level-0 queries);
 //     a CTA owns a CONTIGUOUS range of items (same head, raster-adjacent tiles);
 //   * four window slots in shared memory, one per sampled level (20x28, 16x20, 14x16, 13x14 pixels of 128-byte rows),
 //     each with a `full` mbarrier (TMA transaction bytes) and an `empty` mbarrier (one arrival per consumer warp).  The
 //     producer refills slot l for item n+1 as soon as every consumer warp has finished pass l of item n -- three passes
 //     ahead of its next use;
-//   * a consumer warp owns 8 units of the tile and runs on its own: phase 1 -> records {h_low|w_low, lh, lw, attention}
-//     in its private shared-memory strip -> for each level: wait full, turn h_low / w_low into window offsets, gather
-//     with LDS.128, arrive on empty.  Samples outside the window take predicated global loads (same arithmetic);
+//   * the front-end warps run phase 1 (operand loads, softmax / offset->location in the fused entry, sample geometry) ONE
+//     ITEM AHEAD of the gather and publish records {h_low|w_low, lh, lw, attention} in double-buffered shared-memory
+//     strips, one strip per consumer warp, each with its own full / empty mbarrier pair;
+//   * a consumer warp owns 8 units of the tile: wait for its strip, then for each level: wait `full`, turn h_low / w_low
+//     into window offsets, gather with LDS.128, arrive on `empty`.  Samples outside the window take predicated global
+//     loads (same arithmetic);
 //   * window placement: the tile's geometric image in the sampled level plus the offset the PREVIOUS item of the same
-//     head measured between its samples' mean and its own geometric centre (the heads' directional bias), published by
-//     the consumers with shared atomics during their phase 1 and read by the producer after the `empty` barrier of
-//     level 0 -- so the producer never waits for data of the item it is fetching.
+//     head measured between its samples' mean and its own geometric centre (the heads' directional bias), left in shared
+//     memory by the front end and read by the producer without synchronisation (a stale value only moves a window).
 // Results are bit-identical to every other kernel: level-major accumulation order, the reference's FMUL/FFMA chain in
 // packed fp32x2, zero padding by the TMA unit's out-of-bounds fill, and window placement only decides which of two
 // equivalent load paths a sample takes.  Needs the level geometry on the host (msda_b200_staged_set_host_shapes).
@@ -32,8 +34,12 @@ namespace msda {
 
 namespace {
 
-constexpr int kPlCons = 16;                              // consumer warps
-constexpr int kPlThreads = (kPlCons + 1) * 32;           // + 1 producer warp
+constexpr int kPlCons = 16;                              // consumer (gather) warps
+// front-end (phase 1) warps: the fused entry's phase 1 (softmax, twelve IEEE divisions) is ~490 instructions per strip
+// and needs eight of them to keep up with the gather; the core entry's needs four (and leaves the gather more registers)
+constexpr int kPlFrontMax = 8;
+__host__ __device__ constexpr int pl_front(bool fused) { return fused ? 8 : 4; }
+__host__ __device__ constexpr int pl_threads(bool fused) { return (kPlCons + pl_front(fused) + 1) * 32; }   // + 1 producer warp
 constexpr int kPlUPW = 8;                                // units per consumer warp: 128 units per tile
 constexpr int kPlTH = 8, kPlTWlog2 = 4;                  // 8 x 16 level-0 queries
 constexpr int kPlL = 4, kPlP = 4, kPlLPT = 16;
@@ -43,7 +49,9 @@ __host__ __device__ constexpr int pl_wh(int l) { return l == 0 ? 20 : l == 1 ? 1
 __host__ __device__ constexpr int pl_ww(int l) { return l == 0 ? 28 : l == 1 ? 20 : l == 2 ? 16 : 14; }
 __host__ __device__ constexpr int pl_rows(int l) { return pl_wh(l) * pl_ww(l); }
 __host__ __device__ constexpr int pl_woff(int l) { return l == 0 ? 0 : pl_woff(l - 1) + pl_rows(l - 1) * kPlRowB; }
-constexpr int kPlRecBytes = kPlCons * kPlLPT * kPlUPW * 16;             // 32 KB
+constexpr int kPlRecStrip = kPlLPT * kPlUPW;                           // float4 records of one consumer warp's 8 units
+constexpr int kPlRecBuf = kPlCons * kPlRecStrip * 16;                  // 32 KB: the records of one item
+constexpr int kPlRecBytes = 2 * kPlRecBuf;                             // double-buffered: the front end runs one item ahead
 constexpr int kPlWinBytes = pl_woff(3) + pl_rows(3) * kPlRowB;          // 164608 B
 constexpr int kPlSmem = kPlRecBytes + kPlWinBytes;
 
@@ -59,20 +67,28 @@ template <int OFF> __device__ __forceinline__ uint4 pl_lds128(uint32_t a) {
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const FwdParams p, const __grid_constant__ PipeGeom geo) {
+__global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kernel(const FwdParams p, const __grid_constant__ PipeGeom geo) {
   constexpr int NL = kPlL, PT = kPlP, LPT = kPlLPT, SPL = 4, D = 32;
+  constexpr int kPlFront = pl_front(FUSED);
   extern __shared__ __align__(128) unsigned char pl_smem[];
-  __shared__ __align__(8) unsigned long long sFull[NL], sEmpty[NL];
-  __shared__ int sSum[2][NL][4];      // per item parity, per sampled level: sum h_low, sum w_low, count
+  __shared__ __align__(8) unsigned long long sFull[NL], sEmpty[NL];                        // window slots
+  __shared__ __align__(8) unsigned long long sRecFull[2][kPlCons], sRecEmpty[2][kPlCons];   // record strips
+  // per item parity, per front-end warp, per sampled level: sum h_low, sum w_low, count of its in-range samples.
+  // Plain stores read by the producer one item later; a stale or torn value only moves a window (never a result).
+  __shared__ int sPart[2][kPlFrontMax][NL][3];
   __shared__ int sOrg[2][NL][2];      // per item parity, per sampled level: window origin (h0, w0) chosen by the producer
 
   const int M = p.M, Lq = p.Lq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < 2 * NL * 4) (&sSum[0][0][0])[tid] = 0;
+  if (tid < 2 * kPlFrontMax * NL * 3) (&sPart[0][0][0][0])[tid] = 0;
   if (tid == 0) {
     for (int l = 0; l < NL; ++l) {
       mbar_init(smem_u32(&sFull[l]), 1);
       mbar_init(smem_u32(&sEmpty[l]), kPlCons);
+    }
+    for (int i = 0; i < 2 * kPlCons; ++i) {
+      mbar_init(smem_u32(&sRecFull[0][0] + i), 1);
+      mbar_init(smem_u32(&sRecEmpty[0][0] + i), 1);
     }
     mbar_fence_init();
   }
@@ -96,7 +112,7 @@ __global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const
     gw = __float2int_rd(cx) - (pl_ww(l) - 2) / 2;
   };
 
-  if (warp == kPlCons) {
+  if (warp == kPlCons + kPlFront) {
     // ============================== producer ==============================
     if (lane == 0) {
       int prev_m = -1, prev_gh[NL], prev_gw[NL], prev_h0[NL], prev_w0[NL];
@@ -114,11 +130,17 @@ __global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const
           geo_origin(l, ty, tx, gh, gw);
           int dh = 0, dw = 0;
           if (n >= 1 && m == prev_m) {
-            const int cnt = sSum[(n - 1) & 1][l][2];
+            int sh = 0, sw = 0, cnt = 0;
+#pragma unroll
+            for (int f = 0; f < kPlFront; ++f) {
+              sh += sPart[(n - 1) & 1][f][l][0]; sw += sPart[(n - 1) & 1][f][l][1]; cnt += sPart[(n - 1) & 1][f][l][2];
+            }
             if (cnt > 0) {     // where item n-1 would have wanted its window, relative to its geometric origin
               const float inv = 1.0f / (float)cnt;
-              dh = __float2int_rn((float)sSum[(n - 1) & 1][l][0] * inv) - (pl_wh(l) - 2) / 2 - prev_gh[l];
-              dw = __float2int_rn((float)sSum[(n - 1) & 1][l][1] * inv) - (pl_ww(l) - 2) / 2 - prev_gw[l];
+              dh = __float2int_rn((float)sh * inv) - (pl_wh(l) - 2) / 2 - prev_gh[l];
+              dw = __float2int_rn((float)sw * inv) - (pl_ww(l) - 2) / 2 - prev_gw[l];
+              dh = max(-16, min(16, dh));      // a torn read of the statistics must not throw the window off the tile
+              dw = max(-16, min(16, dw));
             } else {
               dh = prev_h0[l] - prev_gh[l];
               dw = prev_w0[l] - prev_gw[l];
@@ -134,10 +156,6 @@ __global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const
           sOrg[n & 1][l][0] = h0[l];
           sOrg[n & 1][l][1] = w0[l];
         }
-        if (n >= 1) {
-#pragma unroll
-          for (int l = 0; l < NL; ++l) { sSum[(n - 1) & 1][l][0] = 0; sSum[(n - 1) & 1][l][1] = 0; sSum[(n - 1) & 1][l][2] = 0; }
-        }
         prev_m = m;
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
@@ -151,129 +169,148 @@ __global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const
     return;
   }
 
-  // ============================== consumers ==============================
   const int g = lane >> 2, k = lane & 3;                 // unit slot in the warp; lane in the unit = sampled level of its 4 samples
-  float4* sRec = reinterpret_cast<float4*>(pl_smem) + (size_t)warp * LPT * kPlUPW;
-  const float inv_p = 1.0f / (float)PT;
-  const int c0 = k * 16 + (g & 1) * 64;                  // first 16-byte chunk of a row this lane owns; the second is c0 +- 64
-  const int dhi = (g & 1) ? -64 : 64;
-  const int Hk = geo.H[k], Wk = geo.W[k];
-  const float Hf = (float)Hk, Wf = (float)Wk;
-
-  auto locate = [&](int item, bool& valid, size_t& bq, int& m, int& b) {
+  // unit (strip w, slot g) of an item: query pixel, validity, flattened (batch, query) index
+  auto locate = [&](int item, int w, bool& valid, size_t& bq, int& m, int& b) {
     const int tile = item % tiles, bm = item / tiles;
     m = bm % M; b = bm / M;
     const int ty = tile / ntx, tx = tile - ty * ntx;
-    const int j = warp * kPlUPW + g;
+    const int j = w * kPlUPW + g;
     const int y = ty * kPlTH + (j >> kPlTWlog2), x = (tx << kPlTWlog2) + (j & ((1 << kPlTWlog2) - 1));
     valid = (y < geo.H[0]) && (x < geo.W[0]);
     bq = (size_t)b * Lq + (valid ? geo.start[0] + y * geo.W[0] + x : 0);
   };
-  auto prefetch = [&](Prefetched<SPL, 1, FUSED>& pf, size_t bq, int m) {
-    if constexpr (FUSED) {
-      ld_stream_vec<SPL>(p.logits + bq * p.logit_pitch + m * LPT + k * SPL, pf.lg);
-      ld_stream_vec<2 * SPL>(p.offsets + bq * p.off_pitch + (m * LPT + k * SPL) * 2, pf.off);
-      const float* rp = p.ref + (bq * NL + k) * p.ref_dim;
-      if (p.ref_dim == 4) {
-        pf.ref[0] = __ldg(reinterpret_cast<const float4*>(rp));
-      } else {
-        const float2 r2 = __ldg(reinterpret_cast<const float2*>(rp));
-        pf.ref[0] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
-      }
-    } else {
-      const size_t unit = bq * M + m;
-      ld_stream_vec<2 * SPL>(p.loc + (unit * LPT + k * SPL) * 2, pf.xy);
-      ld_stream_vec<SPL>(p.attn + unit * LPT + k * SPL, pf.a);
-    }
-  };
 
-  bool n_valid = false;
-  size_t n_bq = 0;
-  int n_m = 0, n_b = 0;
-  Prefetched<SPL, 1, FUSED> pf;
-  if (count > 0) {
-    locate(first, n_valid, n_bq, n_m, n_b);
-    prefetch(pf, n_bq, n_m);
-  }
-
-  for (int n = 0; n < count; ++n) {
-    const bool valid = n_valid;
-    const int m = n_m, b = n_b;
-    const size_t unit = n_bq * M + m;
-    const uint32_t par = (uint32_t)n & 1u;
-    const char* vhead = reinterpret_cast<const char*>(p.value) + ((size_t)b * p.S * M + m) * kPlRowB;
-
-    // ---------------- phase 1: this lane's 4 samples (all of sampled level k) ----------------
-    {
-      float a[SPL], lx[SPL], ly[SPL];
+  if (warp >= kPlCons) {
+    // ============================== front end: phase 1, one item ahead of the gather ==============================
+    const int f = warp - kPlCons;
+    constexpr int STEPS = kPlCons / kPlFront;            // strips per front-end warp and item
+    const float inv_p = 1.0f / (float)PT;
+    const float Hf = (float)geo.H[k], Wf = (float)geo.W[k];
+    auto prefetch = [&](Prefetched<SPL, 1, FUSED>& pf, size_t bq, int m) {
       if constexpr (FUSED) {
-        float mx = pf.lg[0];
-#pragma unroll
-        for (int i = 1; i < SPL; ++i) mx = fmaxf(mx, pf.lg[i]);
-#pragma unroll
-        for (int off = 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        float v[SPL];
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) { a[i] = expf(__fsub_rn(pf.lg[i], mx)); v[i] = a[i]; }
-#pragma unroll
-        for (int o = LPT / 2; o >= 1; o >>= 1) {
-          if (o >= SPL) {
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], o / SPL));
-          } else {
-            float t[SPL];
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) t[i] = __fadd_rn(v[i], v[i ^ o]);
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) v[i] = t[i];
-          }
-        }
-        const float sum = v[0];
-        const float4 rf = pf.ref[0];
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-          a[i] = __fdiv_rn(a[i], sum);
-          lx[i] = location_from_offset(rf.x, rf.z, pf.off[2 * i], Wf, inv_p, p.ref_dim);
-          ly[i] = location_from_offset(rf.y, rf.w, pf.off[2 * i + 1], Hf, inv_p, p.ref_dim);
+        ld_stream_vec<SPL>(p.logits + bq * p.logit_pitch + m * LPT + k * SPL, pf.lg);
+        ld_stream_vec<2 * SPL>(p.offsets + bq * p.off_pitch + (m * LPT + k * SPL) * 2, pf.off);
+        const float* rp = p.ref + (bq * NL + k) * p.ref_dim;
+        if (p.ref_dim == 4) {
+          pf.ref[0] = __ldg(reinterpret_cast<const float4*>(rp));
+        } else {
+          const float2 r2 = __ldg(reinterpret_cast<const float2*>(rp));
+          pf.ref[0] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
         }
       } else {
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) { lx[i] = pf.xy[2 * i]; ly[i] = pf.xy[2 * i + 1]; a[i] = pf.a[i]; }
+        const size_t unit = bq * M + m;
+        ld_stream_vec<2 * SPL>(p.loc + (unit * LPT + k * SPL) * 2, pf.xy);
+        ld_stream_vec<SPL>(p.attn + unit * LPT + k * SPL, pf.a);
       }
-      int sh = 0, sw = 0, cnt = 0;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        // cuh:285-288 (one FFMA each), cuh:39-45
-        const float h_im = __fmaf_rn(ly[i], Hf, -0.5f);
-        const float w_im = __fmaf_rn(lx[i], Wf, -0.5f);
-        const bool inr = valid && (h_im > -1.0f) && (w_im > -1.0f) && (h_im < Hf) && (w_im < Wf);
-        const float hf = floorf(h_im), wf = floorf(w_im);
-        const int hl = inr ? (int)hf : 0, wl = inr ? (int)wf : 0;
-        if (inr) { sh += hl; sw += wl; ++cnt; }
-        // h_low, w_low >= -1: stored + 1 in 16 bits each; 0xffffffff marks a skipped sample (cuh:288)
-        const uint32_t hw = inr ? (((uint32_t)(hl + 1) << 16) | (uint32_t)(wl + 1)) : 0xffffffffu;
-        sRec[(k * SPL + i) * kPlUPW + (g ^ (2 * k))] =
-            make_float4(__uint_as_float(hw), __fsub_rn(h_im, hf), __fsub_rn(w_im, wf), inr ? a[i] : 0.0f);
-      }
-#pragma unroll
-      for (int o = 4; o <= 16; o <<= 1) {
-        sh += __shfl_xor_sync(0xffffffffu, sh, o);
-        sw += __shfl_xor_sync(0xffffffffu, sw, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      }
-      if (g == 0 && cnt > 0) {
-        atomicAdd(&sSum[par][k][0], sh);
-        atomicAdd(&sSum[par][k][1], sw);
-        atomicAdd(&sSum[par][k][2], cnt);
-      }
-    }
-    __syncwarp();
-
-    // ---------------- next item: operand prefetch ----------------
-    if (n + 1 < count) {
-      locate(first + n + 1, n_valid, n_bq, n_m, n_b);
+    };
+    bool n_valid = false;
+    size_t n_bq = 0;
+    int n_m = 0, n_b = 0;
+    Prefetched<SPL, 1, FUSED> pf;
+    if (count > 0) {
+      locate(first, f, n_valid, n_bq, n_m, n_b);
       prefetch(pf, n_bq, n_m);
     }
+    for (int n = 0; n < count; ++n) {
+      const int buf = n & 1, j = n >> 1;
+      int sh = 0, sw = 0, cnt = 0;
+#pragma unroll 1
+      for (int step = 0; step < STEPS; ++step) {
+        const int w = f + kPlFront * step;
+        const bool valid = n_valid;
+        float a[SPL], lx[SPL], ly[SPL];
+        if constexpr (FUSED) {
+          // softmax over the unit's 16 logits in the operation order of PyTorch's persistent warp softmax
+          // (msda_forward_fast.cu): element e = 4k + i lives in register i of lane k
+          float mx = pf.lg[0];
+#pragma unroll
+          for (int i = 1; i < SPL; ++i) mx = fmaxf(mx, pf.lg[i]);
+#pragma unroll
+          for (int off = 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+          float v[SPL];
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) { a[i] = expf(__fsub_rn(pf.lg[i], mx)); v[i] = a[i]; }
+#pragma unroll
+          for (int o = LPT / 2; o >= 1; o >>= 1) {
+            if (o >= SPL) {
+#pragma unroll
+              for (int i = 0; i < SPL; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], o / SPL));
+            } else {
+              float t[SPL];
+#pragma unroll
+              for (int i = 0; i < SPL; ++i) t[i] = __fadd_rn(v[i], v[i ^ o]);
+#pragma unroll
+              for (int i = 0; i < SPL; ++i) v[i] = t[i];
+            }
+          }
+          const float sum = v[0];
+          const float4 rf = pf.ref[0];
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) {
+            a[i] = __fdiv_rn(a[i], sum);
+            lx[i] = location_from_offset(rf.x, rf.z, pf.off[2 * i], Wf, inv_p, p.ref_dim);
+            ly[i] = location_from_offset(rf.y, rf.w, pf.off[2 * i + 1], Hf, inv_p, p.ref_dim);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) { lx[i] = pf.xy[2 * i]; ly[i] = pf.xy[2 * i + 1]; a[i] = pf.a[i]; }
+        }
+        // operands of the next strip (or of the next item's first strip) are in flight while this one is finished
+        {
+          const int nstep = step + 1 < STEPS ? step + 1 : 0;
+          const int nitem = step + 1 < STEPS ? n : n + 1;
+          if (nitem < count) {
+            locate(first + nitem, f + kPlFront * nstep, n_valid, n_bq, n_m, n_b);
+            prefetch(pf, n_bq, n_m);
+          }
+        }
+        if (n >= 2) mbar_wait(smem_u32(&sRecEmpty[buf][w]), (uint32_t)(j - 1) & 1u);   // the gather of item n-2 released this strip
+        float4* sRec = reinterpret_cast<float4*>(pl_smem + (size_t)buf * kPlRecBuf) + (size_t)w * kPlRecStrip;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          // cuh:285-288 (one FFMA each), cuh:39-45
+          const float h_im = __fmaf_rn(ly[i], Hf, -0.5f);
+          const float w_im = __fmaf_rn(lx[i], Wf, -0.5f);
+          const bool inr = valid && (h_im > -1.0f) && (w_im > -1.0f) && (h_im < Hf) && (w_im < Wf);
+          const float hf = floorf(h_im), wf = floorf(w_im);
+          const int hl = inr ? (int)hf : 0, wl = inr ? (int)wf : 0;
+          if (inr) { sh += hl; sw += wl; ++cnt; }
+          // h_low, w_low >= -1: stored + 1 in 16 bits each; 0xffffffff marks a skipped sample (cuh:288)
+          const uint32_t hw = inr ? (((uint32_t)(hl + 1) << 16) | (uint32_t)(wl + 1)) : 0xffffffffu;
+          sRec[(k * SPL + i) * kPlUPW + (g ^ (2 * k))] =
+              make_float4(__uint_as_float(hw), __fsub_rn(h_im, hf), __fsub_rn(w_im, wf), inr ? a[i] : 0.0f);
+        }
+        if (step == STEPS - 1) {       // placement statistics of this item, before the last strip is published
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1) {
+            sh += __shfl_xor_sync(0xffffffffu, sh, o);
+            sw += __shfl_xor_sync(0xffffffffu, sw, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+          }
+          if (g == 0) { sPart[buf][f][k][0] = sh; sPart[buf][f][k][1] = sw; sPart[buf][f][k][2] = cnt; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sRecFull[buf][w]));
+      }
+    }
+    return;
+  }
+
+  // ============================== consumers: the gather ==============================
+  const int c0 = k * 16 + (g & 1) * 64;                  // first 16-byte chunk of a row this lane owns; the second is c0 +- 64
+  const int dhi = (g & 1) ? -64 : 64;
+  for (int n = 0; n < count; ++n) {
+    bool valid;
+    size_t bq;
+    int m, b;
+    locate(first + n, warp, valid, bq, m, b);
+    const size_t unit = bq * M + m;
+    const uint32_t par = (uint32_t)n & 1u;
+    const int buf = n & 1;
+    const char* vhead = reinterpret_cast<const char*>(p.value) + ((size_t)b * p.S * M + m) * kPlRowB;
+    const float4* sRec = reinterpret_cast<const float4*>(pl_smem + (size_t)buf * kPlRecBuf) + (size_t)warp * kPlRecStrip;
+    mbar_wait(smem_u32(&sRecFull[buf][warp]), (uint32_t)(n >> 1) & 1u);
 
     // ---------------- four level passes ----------------
     f32x2 acc[4];
@@ -319,12 +356,13 @@ __global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const
         accumulate_sample<float, 32, 4>(acc, make_float4(w1, w2, w3, w4), r.w, q[0], q[1], q[2], q[3]);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sEmpty[l]));      // this warp is done with slot l for this item
+      if (lane == 0) mbar_arrive(smem_u32(&sEmpty[l]));      // this warp is done with window slot l for this item
     };
     level_pass(std::integral_constant<int, 0>{});
     level_pass(std::integral_constant<int, 1>{});
     level_pass(std::integral_constant<int, 2>{});
     level_pass(std::integral_constant<int, 3>{});
+    if (lane == 0) mbar_arrive(smem_u32(&sRecEmpty[buf][warp]));   // (after the __syncwarp of pass 3) the strip may be rewritten
     if (valid) {
       char* op = reinterpret_cast<char*>(p.out) + unit * (size_t)(D * 4);
       float f[8];
@@ -333,7 +371,6 @@ __global__ void __launch_bounds__(kPlThreads, 1) msda_fwd_pipelined_kernel(const
       st_stream16(op + c0, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
       st_stream16(op + c0 + dhi, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
     }
-    __syncwarp();   // the record strip is rewritten by the next item's phase 1
   }
 }
 
@@ -346,7 +383,7 @@ int launch_pipelined(const FwdParams& p, const PipeGeom& geo, cudaStream_t strea
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  kern<<<p.grid, kPlThreads, kPlSmem, stream>>>(p, geo);
+  kern<<<p.grid, pl_threads(FUSED), kPlSmem, stream>>>(p, geo);
   return (int)cudaGetLastError();
 }
 
