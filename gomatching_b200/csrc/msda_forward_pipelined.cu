@@ -4,7 +4,7 @@
 // What the staged kernel measured (profiles/r01_s21_*, r01_s22_*): its gather passes run at the L1 pipe's limit and TMA
 // window fills hide, but the per-item front end (phase 1, window placement by a CTA-wide mean, six __syncthreads) does
 // not overlap with anything: 133 us of 390.  Here
-//   * one CTA per SM: 16 consumer (gather) warps + 4 front-end (phase 1) warps + 1 producer warp.  A work item is (frame, head, 8 x 16 tile of level-0 queries);
+//   * one CTA per SM: 16 consumer (gather) warps + 7 front-end (phase 1) warps + 1 producer warp.  A work item is (frame, head, 8 x 16 tile of level-0 queries);
 //     a CTA owns a CONTIGUOUS range of items (same head, raster-adjacent tiles);
 //   * four window slots in shared memory, one per sampled level (20x28, 16x20, 14x16, 13x14 pixels of 128-byte rows),
 //     each with a `full` mbarrier (TMA transaction bytes) and an `empty` mbarrier (one arrival per consumer warp).  The
@@ -35,10 +35,12 @@ namespace msda {
 namespace {
 
 constexpr int kPlCons = 16;                              // consumer (gather) warps
-// front-end (phase 1) warps: the fused entry's phase 1 (softmax, twelve IEEE divisions) is ~490 instructions per strip
-// and needs eight of them to keep up with the gather; the core entry's needs four (and leaves the gather more registers)
+// front-end (phase 1) warps.  The register file is split per scheduler: 16 + 7 + 1 = 24 warps put 6 on each and leave every
+// thread 80 registers; 8 front-end warps (25 warps, 7 on one scheduler) leave 72 and the gather spills (543 us fused),
+// 4 are too few for the fused entry's phase 1 (softmax, twelve IEEE divisions: ~490 instructions per strip; 706 us),
+// 3 too few even for the core entry (482 vs 471 us).  profiles/r01_s3*_pipelined*.log
 constexpr int kPlFrontMax = 8;
-__host__ __device__ constexpr int pl_front(bool fused) { return fused ? 8 : 4; }
+__host__ __device__ constexpr int pl_front(bool) { return 7; }
 __host__ __device__ constexpr int pl_threads(bool fused) { return (kPlCons + pl_front(fused) + 1) * 32; }   // + 1 producer warp
 constexpr int kPlUPW = 8;                                // units per consumer warp: 128 units per tile
 constexpr int kPlTH = 8, kPlTWlog2 = 4;                  // 8 x 16 level-0 queries
@@ -170,21 +172,27 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
   }
 
   const int g = lane >> 2, k = lane & 3;                 // unit slot in the warp; lane in the unit = sampled level of its 4 samples
-  // unit (strip w, slot g) of an item: query pixel, validity, flattened (batch, query) index
-  auto locate = [&](int item, int w, bool& valid, size_t& bq, int& m, int& b) {
+  // an item is (frame b, head m, tile (ty, tx)); decoded once per item (integer divisions), not once per strip
+  struct ItemPos { int b, m, y0, x0; };
+  auto decode = [&](int item) {
+    ItemPos it;
     const int tile = item % tiles, bm = item / tiles;
-    m = bm % M; b = bm / M;
-    const int ty = tile / ntx, tx = tile - ty * ntx;
+    it.m = bm % M; it.b = bm / M;
+    const int ty = tile / ntx;
+    it.y0 = ty * kPlTH; it.x0 = (tile - ty * ntx) << kPlTWlog2;
+    return it;
+  };
+  // unit (strip w, slot g) of an item: validity and flattened (batch, query) index
+  auto locate = [&](const ItemPos& it, int w, bool& valid, size_t& bq) {
     const int j = w * kPlUPW + g;
-    const int y = ty * kPlTH + (j >> kPlTWlog2), x = (tx << kPlTWlog2) + (j & ((1 << kPlTWlog2) - 1));
+    const int y = it.y0 + (j >> kPlTWlog2), x = it.x0 + (j & ((1 << kPlTWlog2) - 1));
     valid = (y < geo.H[0]) && (x < geo.W[0]);
-    bq = (size_t)b * Lq + (valid ? geo.start[0] + y * geo.W[0] + x : 0);
+    bq = (size_t)it.b * Lq + (valid ? geo.start[0] + y * geo.W[0] + x : 0);
   };
 
   if (warp >= kPlCons) {
     // ============================== front end: phase 1, one item ahead of the gather ==============================
     const int f = warp - kPlCons;
-    constexpr int STEPS = kPlCons / kPlFront;            // strips per front-end warp and item
     const float inv_p = 1.0f / (float)PT;
     const float Hf = (float)geo.H[k], Wf = (float)geo.W[k];
     auto prefetch = [&](Prefetched<SPL, 1, FUSED>& pf, size_t bq, int m) {
@@ -206,18 +214,19 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
     };
     bool n_valid = false;
     size_t n_bq = 0;
-    int n_m = 0, n_b = 0;
+    ItemPos cur_it{}, nxt_it{};
     Prefetched<SPL, 1, FUSED> pf;
     if (count > 0) {
-      locate(first, f, n_valid, n_bq, n_m, n_b);
-      prefetch(pf, n_bq, n_m);
+      cur_it = decode(first);
+      locate(cur_it, f, n_valid, n_bq);
+      prefetch(pf, n_bq, cur_it.m);
     }
     for (int n = 0; n < count; ++n) {
       const int buf = n & 1, j = n >> 1;
       int sh = 0, sw = 0, cnt = 0;
+      if (n + 1 < count) nxt_it = decode(first + n + 1);
 #pragma unroll 1
-      for (int step = 0; step < STEPS; ++step) {
-        const int w = f + kPlFront * step;
+      for (int w = f; w < kPlCons; w += kPlFront) {       // this warp's strips of the item
         const bool valid = n_valid;
         float a[SPL], lx[SPL], ly[SPL];
         if constexpr (FUSED) {
@@ -258,11 +267,11 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
         }
         // operands of the next strip (or of the next item's first strip) are in flight while this one is finished
         {
-          const int nstep = step + 1 < STEPS ? step + 1 : 0;
-          const int nitem = step + 1 < STEPS ? n : n + 1;
-          if (nitem < count) {
-            locate(first + nitem, f + kPlFront * nstep, n_valid, n_bq, n_m, n_b);
-            prefetch(pf, n_bq, n_m);
+          const bool same = w + kPlFront < kPlCons;
+          if (same || n + 1 < count) {
+            const ItemPos& it = same ? cur_it : nxt_it;
+            locate(it, same ? w + kPlFront : f, n_valid, n_bq);
+            prefetch(pf, n_bq, it.m);
           }
         }
         if (n >= 2) mbar_wait(smem_u32(&sRecEmpty[buf][w]), (uint32_t)(j - 1) & 1u);   // the gather of item n-2 released this strip
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
           sRec[(k * SPL + i) * kPlUPW + (g ^ (2 * k))] =
               make_float4(__uint_as_float(hw), __fsub_rn(h_im, hf), __fsub_rn(w_im, wf), inr ? a[i] : 0.0f);
         }
-        if (step == STEPS - 1) {       // placement statistics of this item, before the last strip is published
+        if (w + kPlFront >= kPlCons) {   // placement statistics of this item, before the last strip is published
 #pragma unroll
           for (int o = 4; o <= 16; o <<= 1) {
             sh += __shfl_xor_sync(0xffffffffu, sh, o);
@@ -293,6 +302,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sRecFull[buf][w]));
       }
+      cur_it = nxt_it;
     }
     return;
   }
@@ -303,8 +313,9 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
   for (int n = 0; n < count; ++n) {
     bool valid;
     size_t bq;
-    int m, b;
-    locate(first + n, warp, valid, bq, m, b);
+    const ItemPos it = decode(first + n);
+    const int m = it.m, b = it.b;
+    locate(it, warp, valid, bq);
     const size_t unit = bq * M + m;
     const uint32_t par = (uint32_t)n & 1u;
     const int buf = n & 1;
@@ -333,7 +344,8 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
         const bool inwin = ((unsigned)dh <= (unsigned)(pl_wh(l) - 2)) && ((unsigned)dw <= (unsigned)(pl_ww(l) - 2));
         RowVec<32> q[4];
         if (inwin || skipped) {
-          // a skipped sample (attention 0) reads the window's first pixel: finite data, no effect on the sum
+          // a skipped sample (attention 0) reads the window's first pixel: finite data, no effect on the sum.  (Not
+          // loading at all -- a third branch that zeroes the registers -- was measured: 525 vs 476 us.)
           const uint32_t a0 = wbase + (skipped ? 0u : (uint32_t)((dh * pl_ww(l) + dw) * kPlRowB)), a1 = a0 + (uint32_t)dhi;
           q[0].lo = pl_lds128<0>(a0);                              q[0].hi = pl_lds128<0>(a1);
           q[1].lo = pl_lds128<kPlRowB>(a0);                        q[1].hi = pl_lds128<kPlRowB>(a1);
