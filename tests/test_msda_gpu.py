@@ -243,6 +243,28 @@ def test_staged_window_kernel_is_bit_identical(hw, n, dist):
                        g.ms_deform_attn_forward(vb, sh, ls, loc, at, 64))
 
 
+@pytest.mark.parametrize("M,shapes", [(4, [(40, 56), (20, 28), (10, 14), (5, 7)]), (16, [(24, 33), (12, 17), (6, 9), (3, 5)]),
+                                      (8, [(7, 9), (4, 5), (2, 3), (1, 2)])])
+def test_window_kernels_with_other_head_counts_and_odd_maps(M, shapes):
+    """The window kernels take any number of heads (tensor-map dimension M) and odd / tiny pyramids."""
+    import gomatching_b200 as g
+    gen = torch.Generator().manual_seed(M)
+    S = sum(h * w for h, w in shapes)
+    N, L, P, D = 2, 4, 4, 32
+    value = torch.randn(N, S, M, D, generator=gen).cuda()
+    sh = torch.as_tensor(shapes, dtype=torch.long).cuda()
+    lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    ref = torch.rand(N, S, L, 2, generator=gen).cuda()
+    off = (torch.randn(N, S, M, L, P, 2, generator=gen) * 3).cuda()
+    lg = torch.randn(N, S, M, L * P, generator=gen).cuda()
+    loc, attn = g.locations_softmax(sh, ref, off, lg, lanes_per_unit=8)
+    base = g.ms_deform_attn_forward(value, sh, lsi, loc, attn, 64, tuning=dict(mode=1))
+    fbase = g.ms_deform_attn_forward_fused(value, sh, lsi, ref, off, lg, tuning=dict(mode=1))
+    for tn in (dict(mode=4), dict(mode=5)):
+        assert torch.equal(g.ms_deform_attn_forward(value, sh, lsi, loc, attn, 64, tuning=tn), base), tn
+        assert torch.equal(g.ms_deform_attn_forward_fused(value, sh, lsi, ref, off, lg, tuning=tn), fbase), tn
+
+
 # ---------------------------------------------------------------------------------------------------
 # Fused glue: softmax + offsets->locations inside the sampler
 # ---------------------------------------------------------------------------------------------------
