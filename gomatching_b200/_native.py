@@ -140,7 +140,8 @@ _shape_hint_cache = {}
 
 def staged_shape_hint(spatial_shapes, level_start_index) -> None:
     """tuning mode 4: hand the level geometry to the library as host arrays so its window fills can use TMA.
-    One device->host read per distinct shapes tensor (keyed by storage pointer and version), none afterwards."""
+    One device->host read per distinct shapes tensor (keyed by storage pointer and version), none afterwards.  The
+    library keeps the hint per calling thread, and it is set immediately before every mode-4 / mode-5 launch."""
     key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version)
     hit = _shape_hint_cache.get(key)
     if hit is None:

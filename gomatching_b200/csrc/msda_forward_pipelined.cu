@@ -22,7 +22,6 @@
 // Results are bit-identical to every other kernel: level-major accumulation order, the reference's FMUL/FFMA chain in
 // packed fp32x2, zero padding by the TMA unit's out-of-bounds fill, and window placement only decides which of two
 // equivalent load paths a sample takes.  Needs the level geometry on the host (msda_b200_staged_set_host_shapes).
-#include <mutex>
 #include <type_traits>
 #include <string.h>
 #include "msda_fast_common.cuh"

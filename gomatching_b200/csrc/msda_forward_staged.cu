@@ -38,7 +38,6 @@
 // queries vs ~370 us in the fast kernel, 515 vs 494 us per launch (571 vs 543 fused).  Opt-in (tuning.mode = 4).
 // (A head start of 1-8 us for one of the two co-resident CTAs -- in case they ran in lockstep -- changes nothing.)
 #include <cuda.h>
-#include <mutex>
 #include <type_traits>
 #include "msda_fast_common.cuh"
 #include "tma_common.cuh"
@@ -451,16 +450,12 @@ __global__ void __launch_bounds__(kSgThreads, kSgCtasPerSm) msda_fwd_staged_kern
 
 // ---- host side ------------------------------------------------------------------------------------------
 struct HostShapes { bool valid = false; long long hw[kSgL][2]; long long lsi[kSgL]; };
-HostShapes g_host_shapes;
-std::mutex g_host_shapes_mutex;
+// per calling thread: a thread's set_host_shapes + launch sequence cannot be disturbed by another thread's pyramid
+thread_local HostShapes g_host_shapes;
 
 // One 5-D map per sampled level over value (N, S, M, D) fp32: (D, M, W_l, H_l, N), base at the level's first pixel.
 bool make_window_maps(const FwdParams& p, StagedMaps& maps) {
-  HostShapes hs;
-  {
-    std::lock_guard<std::mutex> lock(g_host_shapes_mutex);
-    hs = g_host_shapes;
-  }
+  const HostShapes hs = g_host_shapes;
   EncodeTiledFn fn = tensor_map_encode_fn();
   if (!hs.valid || !fn) return false;
   long long total = 0;
@@ -511,7 +506,6 @@ bool staged_supported(const FwdParams& p) {
 }
 
 void staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host, int L) {
-  std::lock_guard<std::mutex> lock(g_host_shapes_mutex);
   g_host_shapes.valid = false;
   if (!shapes_host || !lsi_host || L != kSgL) return;
   for (int l = 0; l < kSgL; ++l) {
@@ -523,7 +517,6 @@ void staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host,
 }
 
 bool staged_get_host_shapes(long long (*hw)[2], long long* lsi) {
-  std::lock_guard<std::mutex> lock(g_host_shapes_mutex);
   if (!g_host_shapes.valid) return false;
   for (int l = 0; l < kSgL; ++l) {
     hw[l][0] = g_host_shapes.hw[l][0];

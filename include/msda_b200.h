@@ -80,7 +80,8 @@ int         msda_b200_variant_count(void);
 /* Optional hint for tuning.mode = 4: the (H_l, W_l) pairs and level start indices as HOST arrays (L = 4).  With it the
  * staged kernel fills its shared-memory windows with TMA (the tensor maps are encoded on the host and need the level
  * geometry, which the operator API only hands over as a device tensor: ms_deform_attn.py:117-123); without it, or if
- * the hint does not match S, the windows are filled with cp.async.  Pass NULL to clear.  Process-wide, thread-safe. */
+ * the hint does not match S, the windows are filled with cp.async.  Pass NULL to clear.  The hint is stored per calling
+ * thread (set it on the thread that launches). */
 void        msda_b200_staged_set_host_shapes(const int64_t* shapes_host, const int64_t* lsi_host, int L);
 
 /* ---- core operator: the _MSDeformAttnFunction boundary (ms_deform_attn.py:20-27) ------------------ */
