@@ -139,19 +139,23 @@ _shape_hint_cache = {}
 
 
 def staged_shape_hint(spatial_shapes, level_start_index) -> None:
-    """tuning mode 4: hand the level geometry to the library as host arrays so its window fills can use TMA.
-    One device->host read per distinct shapes tensor (keyed by storage pointer and version), none afterwards.  The
-    library keeps the hint per calling thread, and it is set immediately before every mode-4 / mode-5 launch."""
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version)
+    """tuning modes 4 / 5: hand the level geometry to the library as host arrays so its window fills can use TMA.
+    One device->host read per distinct shapes tensor, none afterwards.  The cache entry keeps the two tensors alive,
+    so their identity (and storage pointer) cannot be recycled for another pyramid while the entry exists, and an
+    in-place modification is caught by the version counters.  The library keeps the hint per calling thread, and it is
+    set immediately before every mode-4 / mode-5 launch."""
+    import torch
+    key = (id(spatial_shapes), id(level_start_index))
     hit = _shape_hint_cache.get(key)
-    if hit is None:
+    if (hit is None or hit[0] is not spatial_shapes or hit[1] is not level_start_index
+            or hit[2] != (spatial_shapes._version, level_start_index._version)):
         if len(_shape_hint_cache) > 64:
             _shape_hint_cache.clear()
-        import torch
         sh = spatial_shapes.detach().to("cpu", copy=True).to(dtype=torch.int64).contiguous()
         ls = level_start_index.detach().to("cpu", copy=True).to(dtype=torch.int64).contiguous()
-        hit = _shape_hint_cache[key] = (sh, ls)
-    sh, ls = hit
+        hit = _shape_hint_cache[key] = (spatial_shapes, level_start_index,
+                                        (spatial_shapes._version, level_start_index._version), sh, ls)
+    sh, ls = hit[3], hit[4]
     lib().msda_b200_staged_set_host_shapes(sh.data_ptr(), ls.data_ptr(), int(ls.numel()))
 
 
