@@ -104,3 +104,17 @@ def test_synthetic_shapes_match_the_survey_table():
     N, S, M, D, L, Lq, P = enc.dims
     assert Lq == S
     assert enc.algorithmic_bytes() == 4 * S * 256 + 12 * S * 8 * 16 + 4 * S * 256
+
+
+def test_bench_figures_match_the_survey():
+    """bench.py's algorithmic bytes per launch are SURVEY s8d's B_alg: 68.67 MB per 720p encoder call, 26.02 MB per
+    fp32 decoder call (value counted once, capped by the gather volume)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.algorithmic_bytes(1, 19160, 19160) == 68669440
+    assert bench.algorithmic_bytes(8, 19160, 19160) == 549355520
+    assert bench.algorithmic_bytes(1, 19160, 2500) == 19619840 + 12 * 2500 * 8 * 16 + 4 * 2500 * 256
+    assert abs(bench.algorithmic_bytes(1, 19160, 2500) / 1e6 - 26.02) < 0.01
+    assert (bench.ENC_LAYERS, bench.DEC_LAYERS, bench.HEIGHT, bench.WIDTH) == (6, 6, 720, 1280)
