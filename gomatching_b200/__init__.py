@@ -7,6 +7,7 @@ Public surface (mirrors third_party/adet/layers/ms_deform_attn.py of the referen
     ms_deform_attn_backward      adet._C.ms_deform_attn_backward drop-in
     ms_deform_attn_forward_fused softmax + offsets->locations + sampler in one kernel
     DeformableTransformerEncoderLayer  encoder layer drop-in (sampler + tensor-core feed-forward block)
+    DeformableCompositeTransformerDecoderLayer  point-query decoder layer drop-in
     install_into_adet            monkey-patch the reference's import sites
 """
 from .ms_deform_attn_func import (MSDeformAttnFunction, _MSDeformAttnFunction, fused_supported, locations_softmax,
@@ -14,11 +15,13 @@ from .ms_deform_attn_func import (MSDeformAttnFunction, _MSDeformAttnFunction, f
                                   sample_index)
 from .ms_deform_attn import MSDeformAttn
 from .encoder_layer import DeformableTransformerEncoderLayer
+from .decoder_layer import DeformableCompositeTransformerDecoderLayer
 
 __all__ = [
     "MSDeformAttn", "MSDeformAttnFunction", "_MSDeformAttnFunction", "ms_deform_attn_forward",
     "ms_deform_attn_backward", "ms_deform_attn_forward_fused", "fused_supported", "sample_index",
     "locations_softmax", "install_into_adet", "DeformableTransformerEncoderLayer",
+    "DeformableCompositeTransformerDecoderLayer",
 ]
 
 
@@ -48,4 +51,6 @@ def install_into_adet():
             mod.MSDeformAttn = MSDeformAttn
         if mod is not None and hasattr(mod, "DeformableTransformerEncoderLayer"):
             mod.DeformableTransformerEncoderLayer = DeformableTransformerEncoderLayer
+        if mod is not None and hasattr(mod, "DeformableCompositeTransformerDecoderLayer"):
+            mod.DeformableCompositeTransformerDecoderLayer = DeformableCompositeTransformerDecoderLayer
     return c

@@ -128,3 +128,49 @@ def test_add_layernorm_fallbacks_and_cpu():
     assert torch.equal(add_layernorm(x, y, norm), norm(x + y))
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         add_layernorm(torch.randn(2, 256), None, torch.nn.LayerNorm(256))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Decoder layer drop-in (deformable_transformer.py:326-427)
+# ---------------------------------------------------------------------------------------------------
+DEC_GOLD = os.path.join(HERE, "golden", "decoder_layer_cases.npz")
+DEC_CASES = ["dec_mask", "dec_shared_ref"]
+
+
+def load_dec(name):
+    z = np.load(DEC_GOLD)
+    c = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+    sd = {k[3:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("sd/")}
+    return c, sd
+
+
+def build_dec(c, sd):
+    from gomatching_b200 import DeformableCompositeTransformerDecoderLayer
+    d_model, d_ffn, heads, levels, points = [int(v) for v in c["cfg"]]
+    layer = DeformableCompositeTransformerDecoderLayer(d_model, d_ffn, 0.1, "relu", levels, heads, points).eval()
+    missing, unexpected = layer.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return layer
+
+
+@pytest.mark.parametrize("name", DEC_CASES)
+def test_decoder_layer_state_dict_loads_unchanged(name):
+    c, sd = load_dec(name)
+    layer = build_dec(c, sd)
+    assert sorted(layer.state_dict().keys()) == sorted(sd.keys())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DEC_CASES)
+@pytest.mark.parametrize("fast", [True, False])
+def test_decoder_layer_matches_the_reference_layer_output(name, fast):
+    c, sd = load_dec(name)
+    layer = build_dec(c, sd).cuda()
+    layer.tensor_core_ffn = layer.fused_add_norm = fast
+    layer.attn_cross.tensor_core_projections = fast
+    t = lambda k: torch.from_numpy(c[k]).cuda()
+    mask = t("mask") if c["mask"].size else None
+    with torch.no_grad():
+        out = layer(t("tgt"), t("qpos"), t("ref"), t("src"), t("shapes"), t("lsi"), mask)
+    assert out.shape == tuple(c["out"].shape)
+    assert rel(out.cpu(), torch.from_numpy(c["out"])) <= 1e-4
