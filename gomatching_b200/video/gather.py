@@ -26,11 +26,25 @@ def gather_records(local: torch.Tensor, n_frames: int, dst: int = 0, group=None)
         raise ValueError("rank %d contributes %d slots, expected %d" % (rank, local.shape[0], slots))
     local = local.contiguous()
     bucket: Optional[List[torch.Tensor]] = None
+    out = None
     if rank == dst:
-        bucket = [torch.empty_like(local) for _ in range(world)]
+        out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        bucket = list(out.unbind(0))                       # the ranks' blocks land side by side: no stack afterwards
     dist.gather(local, bucket, dst=dst, group=group)
     if rank != dst:
         return None
-    stacked = torch.stack(bucket, 0)                       # (world, slots, stride)
-    order_r, order_s = zip(*(slot_of_frame(t, world) for t in range(n_frames))) if n_frames else ((), ())
-    return stacked[list(order_r), list(order_s)]
+    return out.view(world * slots, -1).index_select(0, _frame_order(n_frames, world, slots, local.device))
+
+
+_order_cache: dict = {}
+
+
+def _frame_order(n_frames: int, world: int, slots: int, device) -> torch.Tensor:
+    """Row of the (world * slots)-row gather buffer that holds frame t, for t = 0 .. n_frames-1 (cached per device:
+    the tracker rank reorders every chunk with one index_select and no host work)."""
+    key = (n_frames, world, slots, str(device))
+    perm = _order_cache.get(key)
+    if perm is None:
+        rows = [r * slots + s for r, s in (slot_of_frame(t, world) for t in range(n_frames))]
+        perm = _order_cache[key] = torch.tensor(rows, dtype=torch.long, device=device)
+    return perm
