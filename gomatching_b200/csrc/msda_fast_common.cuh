@@ -136,6 +136,39 @@ __device__ __forceinline__ void accumulate_sample(f32x2 (&acc)[NP], const float4
   }
 }
 
+// Softmax over the LPT logits of one unit, spread over LPR lanes with SPL = LPT / LPR consecutive elements per lane
+// (element e = k * SPL + i lives in register i of lane k), in the operation order of PyTorch's persistent warp softmax
+// for <= 32 elements: one element per virtual lane, xor butterfly over the element index LPT/2 .. 1.  Index bits
+// >= log2(SPL) are lane bits (shuffle), the rest are register bits (in-lane pairs); fp32 addition is commutative, so
+// both partners of a step get the same sum.  Returns the un-normalised exponentials in e[] and their sum -- the caller
+// divides (IEEE), like the reference's softmax (ms_deform_attn.py:138-139).  All 32 lanes must call it.
+template <int SPL, int LPR, int LPT>
+__device__ __forceinline__ float unit_softmax_terms(const float (&lg)[SPL], float (&e)[SPL]) {
+  static_assert(fast_next_pow2(LPT) == LPT && LPT <= 32 && SPL * LPR == LPT, "L*P must be a power of two <= 32");
+  float mx = lg[0];
+#pragma unroll
+  for (int i = 1; i < SPL; ++i) mx = fmaxf(mx, lg[i]);
+#pragma unroll
+  for (int off = LPR / 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float v[SPL];
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) { e[i] = expf(__fsub_rn(lg[i], mx)); v[i] = e[i]; }
+#pragma unroll
+  for (int o = LPT / 2; o >= 1; o >>= 1) {
+    if (o >= SPL) {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], o / SPL));
+    } else {
+      float t[SPL];
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) t[i] = __fadd_rn(v[i], v[i ^ o]);
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) v[i] = t[i];
+    }
+  }
+  return v[0];
+}
+
 // Raw operands of one lane's SPL samples between the prefetch and phase 1.
 template <int SPL, int NLV, bool FUSED> struct Prefetched;
 template <int SPL, int NLV> struct Prefetched<SPL, NLV, false> {

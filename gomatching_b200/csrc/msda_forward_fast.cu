@@ -197,34 +197,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
     {
       float a[SPL], lx[SPL], ly[SPL];
       if constexpr (FUSED) {
-        // softmax over the unit's LPT logits in the operation order of PyTorch's persistent warp softmax for
-        // <= 32 elements: one element per virtual lane, xor butterfly over the element index WS/2 .. 1.  Element
-        // e = k*SPL + i lives in register i of lane k: index bits >= log2(SPL) are lane bits (shuffle), the rest
-        // are register bits (in-lane pairs).  fp32 addition is commutative, so both partners get the same sum.
-        constexpr int WS = fast_next_pow2(LPT);
-        static_assert(WS == LPT && WS <= 32, "fused fast path: L*P must be a power of two <= 32");
-        float mx = pf.lg[0];
-#pragma unroll
-        for (int i = 1; i < SPL; ++i) mx = fmaxf(mx, pf.lg[i]);
-#pragma unroll
-        for (int off = LPR / 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        float v[SPL];
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) { a[i] = expf(__fsub_rn(pf.lg[i], mx)); v[i] = a[i]; }
-#pragma unroll
-        for (int o = WS / 2; o >= 1; o >>= 1) {
-          if (o >= SPL) {
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], o / SPL));
-          } else {
-            float t[SPL];
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) t[i] = __fadd_rn(v[i], v[i ^ o]);
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) v[i] = t[i];
-          }
-        }
-        const float sum = v[0];
+        // softmax over the unit's LPT logits in PyTorch's operation order (msda_fast_common.cuh)
+        const float sum = unit_softmax_terms<SPL, LPR, LPT>(pf.lg, a);
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
           const int l = lvl0 + i / PT;

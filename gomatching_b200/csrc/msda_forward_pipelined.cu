@@ -233,28 +233,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
         if constexpr (FUSED) {
           // softmax over the unit's 16 logits in the operation order of PyTorch's persistent warp softmax
           // (msda_forward_fast.cu): element e = 4k + i lives in register i of lane k
-          float mx = pf.lg[0];
-#pragma unroll
-          for (int i = 1; i < SPL; ++i) mx = fmaxf(mx, pf.lg[i]);
-#pragma unroll
-          for (int off = 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-          float v[SPL];
-#pragma unroll
-          for (int i = 0; i < SPL; ++i) { a[i] = expf(__fsub_rn(pf.lg[i], mx)); v[i] = a[i]; }
-#pragma unroll
-          for (int o = LPT / 2; o >= 1; o >>= 1) {
-            if (o >= SPL) {
-#pragma unroll
-              for (int i = 0; i < SPL; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], o / SPL));
-            } else {
-              float t[SPL];
-#pragma unroll
-              for (int i = 0; i < SPL; ++i) t[i] = __fadd_rn(v[i], v[i ^ o]);
-#pragma unroll
-              for (int i = 0; i < SPL; ++i) v[i] = t[i];
-            }
-          }
-          const float sum = v[0];
+          const float sum = unit_softmax_terms<SPL, 4, LPT>(pf.lg, a);
           const float4 rf = pf.ref[0];
 #pragma unroll
           for (int i = 0; i < SPL; ++i) {
