@@ -3,6 +3,7 @@
 // per-sample arithmetic two channels at a time.
 #pragma once
 #include "msda_device.cuh"
+#include "msda_launch.h"
 
 namespace msda {
 
@@ -180,5 +181,32 @@ template <int SPL, int NLV> struct Prefetched<SPL, NLV, true> {
   float lg[SPL];
   float4 ref[NLV];
 };
+
+// Issue the streaming loads of one lane's phase-1 operands: samples first .. first+SPL-1 of unit (bq, m), where
+// bq = batch * Lq + query.  Core entry: sampling locations and attention weights; fused entry: raw offsets, logits and
+// the reference point(s) of the NLV levels the samples span (first level lvl0).  NL levels, LPT = L * P samples.
+template <int SPL, int NLV, bool FUSED, int LPT, int NL>
+__device__ __forceinline__ void load_unit_operands(Prefetched<SPL, NLV, FUSED>& pf, const FwdParams& p, size_t bq, int m,
+                                                   int first, int lvl0) {
+  if constexpr (FUSED) {
+    // rows of offsets / logits may be slices of one merged projection output (pitch > dense row length)
+    ld_stream_vec<SPL>(p.logits + bq * p.logit_pitch + m * LPT + first, pf.lg);
+    ld_stream_vec<2 * SPL>(p.offsets + bq * p.off_pitch + (m * LPT + first) * 2, pf.off);
+#pragma unroll
+    for (int j = 0; j < NLV; ++j) {
+      const float* rp = p.ref + (bq * NL + lvl0 + j) * p.ref_dim;
+      if (p.ref_dim == 4) {
+        pf.ref[j] = __ldg(reinterpret_cast<const float4*>(rp));
+      } else {
+        const float2 r2 = __ldg(reinterpret_cast<const float2*>(rp));
+        pf.ref[j] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
+      }
+    }
+  } else {
+    const size_t unit = bq * p.M + m;
+    ld_stream_vec<2 * SPL>(p.loc + (unit * LPT + first) * 2, pf.xy);
+    ld_stream_vec<SPL>(p.attn + unit * LPT + first, pf.a);
+  }
+}
 
 }  // namespace msda

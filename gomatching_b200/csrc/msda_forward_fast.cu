@@ -155,25 +155,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
     bq = (size_t)t_b * Lq + (valid ? qi : 0);
     unit = bq * M + t_m;
   };
-  auto prefetch = [&](Prefetched<SPL, NLV, FUSED>& pf, size_t bq, size_t unit) {
-    if constexpr (FUSED) {
-      // rows of offsets / logits may be slices of one merged projection output (pitch > dense row length)
-      ld_stream_vec<SPL>(p.logits + bq * p.logit_pitch + t_m * LPT + k * SPL, pf.lg);
-      ld_stream_vec<2 * SPL>(p.offsets + bq * p.off_pitch + (t_m * LPT + k * SPL) * 2, pf.off);
-#pragma unroll
-      for (int j = 0; j < NLV; ++j) {
-        const float* rp = p.ref + (bq * NL + lvl0 + j) * p.ref_dim;
-        if (p.ref_dim == 4) {
-          pf.ref[j] = __ldg(reinterpret_cast<const float4*>(rp));
-        } else {
-          const float2 r2 = __ldg(reinterpret_cast<const float2*>(rp));
-          pf.ref[j] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
-        }
-      }
-    } else {
-      ld_stream_vec<2 * SPL>(p.loc + (unit * LPT + k * SPL) * 2, pf.xy);
-      ld_stream_vec<SPL>(p.attn + unit * LPT + k * SPL, pf.a);
-    }
+  auto prefetch = [&](Prefetched<SPL, NLV, FUSED>& pf, size_t bq, size_t /*unit*/) {
+    load_unit_operands<SPL, NLV, FUSED, LPT, NL>(pf, p, bq, t_m, k * SPL, lvl0);
   };
 
   bool have = tile < tile_end;

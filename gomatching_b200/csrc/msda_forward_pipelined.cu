@@ -197,21 +197,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
     const float inv_p = 1.0f / (float)PT;
     const float Hf = (float)geo.H[k], Wf = (float)geo.W[k];
     auto prefetch = [&](Prefetched<SPL, 1, FUSED>& pf, size_t bq, int m) {
-      if constexpr (FUSED) {
-        ld_stream_vec<SPL>(p.logits + bq * p.logit_pitch + m * LPT + k * SPL, pf.lg);
-        ld_stream_vec<2 * SPL>(p.offsets + bq * p.off_pitch + (m * LPT + k * SPL) * 2, pf.off);
-        const float* rp = p.ref + (bq * NL + k) * p.ref_dim;
-        if (p.ref_dim == 4) {
-          pf.ref[0] = __ldg(reinterpret_cast<const float4*>(rp));
-        } else {
-          const float2 r2 = __ldg(reinterpret_cast<const float2*>(rp));
-          pf.ref[0] = make_float4(r2.x, r2.y, 0.0f, 0.0f);
-        }
-      } else {
-        const size_t unit = bq * M + m;
-        ld_stream_vec<2 * SPL>(p.loc + (unit * LPT + k * SPL) * 2, pf.xy);
-        ld_stream_vec<SPL>(p.attn + unit * LPT + k * SPL, pf.a);
-      }
+      load_unit_operands<SPL, 1, FUSED, LPT, NL>(pf, p, bq, m, k * SPL, k);
     };
     bool n_valid = false;
     size_t n_bq = 0;
