@@ -1,0 +1,252 @@
+"""Clip driver for a reference-API video model: frame-sharded spotting, per-round record gather, and the reference's
+sequential LST-Matcher association overlapped with the next round's spotting.
+
+Takes the place of (reference, one process, one frame at a time):
+    eval.py:329-345                       chunk loop, ``video_text_spotter(frames, instances, batch_id, id_count, ...)``
+    GoMBatchPredictor.__call__            gomatching/text_track_visualizer.py:295-335   host preprocessing, last-batch
+                                          ``_remove_short_track`` + ``batch_postprocess``
+    GoMatching.batch_inference            gomatching/modeling/meta_arch/gom_lstmatcher.py:366-403
+
+The model is used through the reference's own methods and nothing else:
+    model.inference([frame], time_cost)            -> frame-local spotting (:268-351), N = 1 per forward
+    model.run_short_term_match / run_long_term_match / test_len   (:405-564) via ``reference_association_step``
+    model._remove_short_track, model.batch_postprocess            (:566-577, :353-364)
+so the tracker code is the reference's, unchanged, and sees the same tensors in the same order as in the serial loop.
+
+Schedule.  The clip is cut into ROUNDS.  In a round rank r spots ``weights[r]`` consecutive frames; the ranks' records
+are gathered to the tracker rank (one collective per round), which appends them IN FRAME ORDER to a queue.  A worker
+thread on the tracker rank -- its own CUDA stream, ``torch.no_grad`` -- pops frames and runs the association step, so
+round k is associated while all ranks (the tracker rank included) spot round k+1.  ``weights`` lets the tracker rank
+take fewer frames per round when the association is the longer pole (SURVEY.md s8e "scaling limiter").
+"""
+from __future__ import annotations
+
+import queue
+import sys
+import threading
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .pipeline import _world, reference_association_step
+from .records import RecordSchema
+
+__all__ = ["round_plan", "ClipTracker"]
+
+
+def round_plan(n_frames: int, weights: Sequence[int]) -> List[List[Tuple[int, int, int]]]:
+    """Frame -> (rank, slot) assignment.  Returns the rounds; a round is a list of (frame, rank, slot) in frame order.
+    With all weights 1 this is ``frame t -> rank t mod W`` (sharding.frame_owner)."""
+    if any(w < 0 for w in weights) or sum(weights) <= 0:
+        raise ValueError("weights must be non-negative with a positive sum, got %r" % (list(weights),))
+    per_round = sum(weights)
+    owner: List[Tuple[int, int]] = []
+    for r, w in enumerate(weights):
+        owner.extend((r, s) for s in range(w))
+    rounds = []
+    for start in range(0, n_frames, per_round):
+        rounds.append([(t, *owner[t - start]) for t in range(start, min(start + per_round, n_frames))])
+    return rounds
+
+
+class _Association(threading.Thread):
+    """Tracker-rank worker: consumes gathered rounds in order and runs the reference's ID assignment."""
+
+    def __init__(self, tracker: "ClipTracker"):
+        super().__init__(daemon=True, name="lst-matcher")
+        self.t = tracker
+        self.q: "queue.Queue" = queue.Queue()
+        self.error: Optional[BaseException] = None
+        self.busy_s = 0.0
+        self.stream = torch.cuda.Stream(device=tracker.device) if tracker.device.type == "cuda" else None
+
+    def run(self):
+        try:
+            with torch.no_grad():
+                if self.stream is not None:
+                    with torch.cuda.device(self.t.device), torch.cuda.stream(self.stream):
+                        self._loop()
+                else:
+                    self._loop()
+        except BaseException as e:  # surfaced by ClipTracker.finish()
+            self.error = e
+
+    def _loop(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            records, frames, ready = item
+            if ready is not None:
+                self.stream.wait_event(ready)
+            t0 = time.perf_counter()
+            self.t._associate_round(records, frames)
+            if self.stream is not None:
+                self.stream.synchronize()
+            self.busy_s += time.perf_counter() - t0
+
+
+class ClipTracker:
+    """One per process.  ``feed(frames)`` any number of times (a reference "chunk" or the whole clip), then
+    ``finish()`` -> on the tracker rank the per-frame results ``[{"instances": Instances}, ...]`` with ``track_ids``
+    (what GoMBatchPredictor returns after the last batch); None on the other ranks."""
+
+    def __init__(self, model, schema: Optional[RecordSchema] = None, weights: Optional[Sequence[int]] = None,
+                 tracker_rank: int = 0, overlap: bool = True, group=None, frame_size: Optional[Tuple[int, int]] = None,
+                 use_batcher: Optional[bool] = None, input_format: str = "RGB"):
+        self.model = model
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.weights = list(weights) if weights is not None else [1] * self.world
+        if len(self.weights) != self.world:
+            raise ValueError("need one weight per rank (%d), got %d" % (self.world, len(self.weights)))
+        self.tracker_rank = tracker_rank
+        self.device = torch.device(getattr(model, "device", "cpu"))
+        self.use_batcher = self.device.type == "cuda" if use_batcher is None else use_batcher
+        self.input_format = input_format
+        mod = sys.modules[type(model).__module__]
+        self._Instances, self._Boxes, self._ImageList = mod.Instances, mod.Boxes, mod.ImageList
+        nq = int(model.cfg.MODEL.TRANSFORMER.NUM_QUERIES) if hasattr(model, "cfg") else 100
+        self.schema = schema or RecordSchema(max_instances=nq)
+        self.max_slots = max(self.weights)
+        self.frame_size = frame_size
+        # running state of the tracker rank (the arguments batch_inference threads through, eval.py:333-344)
+        self.instances: list = []
+        self.id_count = 0
+        self.n_fed = 0
+        self.time_cost = {k: 0 for k in ("total_time", "pre_process", "backbone", "detector", "rescore", "tracker",
+                                         "long_match", "short_match", "post_process")}
+        self.spot_s = 0.0
+        self.assoc_inline_s = 0.0
+        self._worker: Optional[_Association] = None
+        if overlap and self.rank == tracker_rank:
+            self._worker = _Association(self)
+            self._worker.start()
+        if self.use_batcher:
+            self._install_batcher()
+
+    # ------------------------------------------------------------------------------------------ spotting
+    def _install_batcher(self):
+        """Replace the model's host-side float conversion + eager normalise/pad (text_track_visualizer.py:315-321,
+        gom_lstmatcher.py:159-170) by the frame-batcher kernel on the uint8 frame; values are bit-identical."""
+        from .batcher import batch_frames
+
+        cfg = self.model.cfg
+        mean, std = list(cfg.MODEL.PIXEL_MEAN), list(cfg.MODEL.PIXEL_STD)
+        flip = self.input_format == "RGB"
+        ImageList = self._ImageList
+
+        def preprocess_image(batched_inputs):
+            frames = [x["image"] for x in batched_inputs]
+            if any(f.dtype != torch.uint8 or f.dim() != 3 or f.shape[-1] != 3 for f in frames):
+                raise ValueError("the B200 frame batcher takes uint8 (H, W, 3) frames as decoded")
+            if len({tuple(f.shape) for f in frames}) != 1:
+                raise ValueError("frames of one forward must share a size")
+            batch = batch_frames(torch.stack(frames) if len(frames) > 1 else frames[0], mean, std, flip_channels=flip)
+            return ImageList(batch, [tuple(f.shape[:2]) for f in frames])
+
+        self.model.preprocess_image = preprocess_image
+
+    def _to_input(self, frame):
+        """One frame as the predictor hands it to the model.  With the batcher: the uint8 HWC frame itself (BGR, as
+        read); otherwise the reference's host conversion (optional RGB flip, float32 CHW)."""
+        if self.use_batcher:
+            t = frame if isinstance(frame, torch.Tensor) else torch.from_numpy(frame)
+            h, w = t.shape[:2]
+            return {"image": t.to(self.device, non_blocking=True), "height": h, "width": w, "video_id": 0}
+        if isinstance(frame, dict):
+            return frame
+        x = frame.numpy() if isinstance(frame, torch.Tensor) else frame
+        if self.input_format == "RGB":
+            x = x[:, :, ::-1]
+        h, w = x.shape[:2]
+        return {"image": torch.as_tensor(x.astype("float32").transpose(2, 0, 1)), "height": h, "width": w,
+                "video_id": 0}
+
+    def _spot(self, frame) -> Tuple[Dict[str, torch.Tensor], Tuple[int, int]]:
+        inst = self.model.inference([self._to_input(frame)], self.time_cost)[0]
+        fields = {k: (v.tensor if isinstance(v, self._Boxes) else v) for k, v in inst.get_fields().items()}
+        return fields, tuple(int(s) for s in inst.image_size)
+
+    # ------------------------------------------------------------------------------------------ association
+    def _associate_round(self, records: torch.Tensor, frames: List[int]):
+        for row, t in zip(records, frames):
+            fields, frame_index, size = self.schema.unpack(row)
+            assert frame_index == t == len(self.instances), "gather lost the frame order"
+            inst = self._Instances(size)
+            for k, v in fields.items():
+                inst.set(k, self._Boxes(v) if k == "pred_boxes" else v)
+            self.instances.append(inst)
+            self.instances, self.id_count = reference_association_step(self.model, self.instances, t, self.id_count)
+
+    # ------------------------------------------------------------------------------------------ driver
+    @torch.no_grad()
+    def feed(self, frames: Sequence) -> None:
+        """Spot and associate ``frames`` (numpy / torch uint8 HWC BGR as decoded, or -- without the batcher -- the
+        reference's input dicts).  Every rank passes the same list; a rank only touches the frames it owns."""
+        base = self.n_fed
+        for rnd in round_plan(len(frames), self.weights):
+            t0 = time.perf_counter()
+            block = self.schema.empty(self.max_slots, device=self.device)
+            for t, r, s in rnd:
+                if r == self.rank:
+                    fields, size = self._spot(frames[t])
+                    self.schema.pack_into(block[s], fields, base + t, size)
+            self.spot_s += time.perf_counter() - t0
+            gathered = self._gather(block)
+            if self.rank != self.tracker_rank:
+                continue
+            rows = torch.stack([gathered[r, s] for _, r, s in rnd]) if self.world > 1 else gathered[0, :len(rnd)]
+            ids = [base + t for t, _, _ in rnd]
+            if self._worker is not None:
+                ready = None
+                if self.device.type == "cuda":
+                    ready = torch.cuda.Event()
+                    ready.record()
+                    rows.record_stream(self._worker.stream)
+                self._worker.q.put((rows, ids, ready))
+                if self._worker.error is not None:
+                    raise self._worker.error
+            else:
+                t1 = time.perf_counter()
+                self._associate_round(rows, ids)
+                self.assoc_inline_s += time.perf_counter() - t1
+        self.n_fed += len(frames)
+
+    def _gather(self, block: torch.Tensor) -> Optional[torch.Tensor]:
+        """(max_slots, stride) per rank -> (world, max_slots, stride) on the tracker rank."""
+        if self.world == 1:
+            return block.unsqueeze(0)
+        out, bucket = None, None
+        if self.rank == self.tracker_rank:
+            out = torch.empty((self.world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
+            bucket = list(out.unbind(0))
+        dist.gather(block, bucket, dst=self.tracker_rank, group=self.group)
+        return out
+
+    def drain(self) -> None:
+        """Block until every fed frame has been associated (tracker rank; no-op elsewhere).  Ends the worker."""
+        if self._worker is not None:
+            self._worker.q.put(None)                     # in-order sentinel: everything queued before it is processed
+            self._worker.join()
+            err, self.assoc_worker_s = self._worker.error, self._worker.busy_s
+            self._worker = None
+            if err is not None:
+                raise err
+
+    @torch.no_grad()
+    def finish(self, image_size: Optional[Tuple[int, int]] = None):
+        """Last-batch post-processing of GoMBatchPredictor.__call__ (text_track_visualizer.py:326-331)."""
+        self.drain()
+        if self.rank != self.tracker_rank:
+            return None
+        instances = self.instances
+        if self.model.min_track_len > 0:
+            instances = self.model._remove_short_track(instances)
+        size = image_size or (instances[0].image_size if instances else (0, 0))
+        return self.model.batch_postprocess(instances, [size for _ in range(len(instances))])
+
+    def association_seconds(self) -> float:
+        return getattr(self, "assoc_worker_s", 0.0) + self.assoc_inline_s + (self._worker.busy_s if self._worker else 0.0)
