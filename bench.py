@@ -1,28 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- the MSDeformAttn hot path of GoMatching/DeepSolo on B200, one JSON line.
+"""bench.py -- GoMatching's video hot path on B200: DeepSolo + LST-Matcher frames/s, MSDeformAttn HBM GB/s.  One JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload clip|op]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], with configs[2]'s decoder shape riding along): one STEP is the
-MSDeformAttn hot path of a batch of F = 8 synthetic 1280x720 DeepSolo-R50 frames per GPU -- 6 encoder
-self-attention calls (Lq = S = 19160 tokens) + 6 point-query decoder cross-attention calls
-(Lq = 100 x 25 = 2500), d_model 256, 8 heads, 4 levels, 4 points, fp32 -- each call doing the four things
-north_star names: offset->location math, softmax over levels x points, multi-level bilinear gather,
-weighted reduction.  metric = frames/s (frames whose hot path completed per second, whole job).
-
-  value      inputs resident in HBM; CUDA events; max over ranks
-  e2e        same work through the public API with HOST (pinned) buffers: H2D of every input and D2H of
-             every output inside the timed region
-  roofline   dominant kernel = the encoder-shape launch; achieved = SURVEY.md s8(d) algorithmic bytes per
-             launch / its mean CUDA-event duration inside the timed region; peak = MEASURED_PEAKS.json
-  cpu_baseline  the reference's CPU path (ms_deform_attn_core_pytorch -> F.grid_sample, restated in
-             oracle/msda_oracle.py because the reference's Python cannot travel to the GPU box) on the
-             box's host cores, bounded sample
-  --impl reference   that CPU path as its own arm (rank 0 only under torchrun)
-
-L2 hygiene: every launch works on buffers larger than L2 (one encoder call at F=8 touches 549 MB, one
-decoder call 208 MB, L2 is 126 MB) and consecutive launches use different buffer sets.
+Workload "clip" (default; BASELINE.json metric "frames/sec (DeepSolo+LST, 1280x720)", configs[3]): the reference's OWN
+GoMatching model -- ResNet-50 + 6+6-layer DeepSolo spotter + LSTMatcher, default-initialised and seeded, imported
+unmodified from baseline/_ref (tools/refhost) -- with the B200 operator stack installed
+(``gomatching_b200.install_into_adet``), driven by ``gomatching_b200.video.ClipTracker``: frames sharded over the
+ranks, one record gather per round to rank 0, the reference's sequential tracker (unchanged) INSIDE the timed loop,
+overlapped with the next round's spotting.  One STEP = one round = ``--frames`` 1280x720 frames per spotting rank.
+  value      frames/s, uint8 frames resident in HBM when the timed region starts; CUDA events; max over ranks
+  e2e        same through the public API with HOST frames: pinned uint8 frame H2D per frame and the frame's track
+             ids D2H inside the timed region
+  spotting_only   the same loop without the association (what scales with the GPU count; the tracker is the serial term)
+Workload "op" (round 1's line; also measured in every clip run as ``msda``): the MSDeformAttn calls of F = 8 frames per
+GPU, 6 encoder (Lq = S = 19160) + 6 decoder (Lq = 2500) launches per step on buffers larger than L2, fp32.
+  roofline   dominant kernel of the path = the encoder-shape sampler launch; achieved = SURVEY.md s8(d) algorithmic
+             bytes per launch / its mean CUDA-event duration inside that timed region; peak = MEASURED_PEAKS.json.
+             ``roofline.in_pipeline`` = the same kernel timed live inside the clip's model forward (N = 1, value just
+             written by value_proj, i.e. L2-warm).
+  cpu_baseline / --impl reference   the reference's CPU implementation on the box's host cores, bounded sample:
+             clip = the unmodified reference model end to end on one frame per step (MSDeformAttn via
+             ms_deform_attn_core_pytorch, BASELINE.json configs[0]; kind "reference");
+             op = 6 + 6 core_pytorch calls of one frame (kind "port", oracle.core_gridsample).
 """
 from __future__ import annotations
 
@@ -51,20 +52,35 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per step per GPU")
+    ap.add_argument("--workload", default="auto", choices=["auto", "clip", "op"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (clip: 4, op: 8)")
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--level", default="layers", choices=["op", "module", "layers"], help="install_into_adet level (clip)")
+    ap.add_argument("--tracker-frames", type=int, default=-1,
+                    help="frames per step the tracker rank spots itself (clip, N > 1); -1 = same as the others")
     ap.add_argument("--dist", default="local", choices=["local", "uniform", "oor", "center"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--unfused", action="store_true", help="time the core operator (loc/attn precomputed)")
+    ap.add_argument("--no-sublines", action="store_true", help="skip the F=1 / 1080p / reference-kernel sub-lines")
+    ap.add_argument("--unfused", action="store_true", help="op: time the core operator (loc/attn precomputed)")
     ap.add_argument("--tuning", default="", help="k=v,... msda_b200_tuning_t overrides for the encoder launch")
     return ap.parse_args()
+
+
+def clip_available():
+    try:
+        from tools.refhost import loader
+        return loader.reference_root() is not None
+    except Exception:
+        return False
 
 
 # ---------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+    """nvidia-smi sampled every 100 ms while the timed regions run (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -77,7 +93,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -91,7 +107,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -113,92 +129,154 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU reference path (oracle port of ms_deform_attn_core_pytorch + the eager glue) -- checker / baseline only
+# configs (identical for both arms: built from the arguments only)
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_frame_seconds(repeats: int, dist: str):
-    """Times 1 encoder + 1 decoder MSDeformAttn call of ONE frame on the host; returns
-    (seconds per frame = 6*t_enc + 6*t_dec, t_enc, t_dec, threads)."""
+def clip_config(args):
+    return {
+        "workload": "clip%dp: synthetic %dx%d uint8 clip through the reference's GoMatching (ResNet-50 + DeepSolo 6+6 layers, "
+                    "100 point-query proposals x 25 points, d=256, 8 heads, 4 levels, 4 points + LSTMatcher tracker in the "
+                    "loop), default-initialised seeded weights, 1 frame per forward" % (args.height, args.width, args.height),
+        "frame": "%dx%d" % (args.width, args.height),
+        "l2": "every frame's forward streams > L2 of activations (the encoder feed-forward intermediate alone is 78 MB "
+              "per layer); the op-level lines rotate buffer sets larger than L2",
+    }
+
+
+def op_config(args):
+    return {
+        "workload": "MSDeformAttn hot path per 1280x720 DeepSolo-R50 frame: 6 encoder self-attn (Lq=S=19160, 4 levels "
+                    "90x160..12x20) + 6 point-query decoder cross-attn (Lq=100x25) forwards, d=256, 8 heads, 4 points",
+        "sampling_distribution": args.dist,
+        "l2": "inputs larger than L2 (549 MB per encoder launch, 208 MB per decoder launch at 8 frames; buffer sets rotate)",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference paths -- baselines only
+# ---------------------------------------------------------------------------------------------------
+def cpu_op_frame_seconds(repeats: int, dist: str):
+    """The reference's CPU path of the operator (ms_deform_attn_core_pytorch -> F.grid_sample, restated in
+    oracle/msda_oracle.py) on ALL 6 + 6 calls of one 1280x720 frame; returns (median seconds per frame, threads)."""
     import torch
     from gomatching_b200 import synthetic as syn
     from oracle import msda_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
     threads = torch.get_num_threads()
-    out = {}
-    for kind in ("encoder", "decoder"):
-        w = syn.make_workload(kind, HEIGHT, WIDTH, n=1, seed=0, dist=dist)
-        wh = torch.stack([w.shapes[:, 1], w.shapes[:, 0]], -1)
+    ws = {kind: syn.make_workload(kind, HEIGHT, WIDTH, n=1, seed=0, dist=dist) for kind in ("encoder", "decoder")}
 
-        def call():
-            attn = torch.softmax(w.logits, -1).view(w.attn.shape)                          # ms_deform_attn.py:139
-            loc = w.ref[:, :, None, :, None, :] + w.offsets / wh[None, None, None, :, None, :]   # :143-144
-            return O.core_gridsample(w.value, w.shapes.tolist(), loc, attn)                # :40-60
-        call()
-        ts = []
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            call()
-            ts.append(time.perf_counter() - t0)
-        out[kind] = statistics.median(ts)
-    return ENC_LAYERS * out["encoder"] + DEC_LAYERS * out["decoder"], out["encoder"], out["decoder"], threads
+    def call(w):
+        wh = torch.stack([w.shapes[:, 1], w.shapes[:, 0]], -1)
+        attn = torch.softmax(w.logits, -1).view(w.attn.shape)                          # ms_deform_attn.py:139
+        loc = w.ref[:, :, None, :, None, :] + w.offsets / wh[None, None, None, :, None, :]   # :143-144
+        return O.core_gridsample(w.value, w.shapes.tolist(), loc, attn)                # :40-60
+
+    def frame():
+        for _ in range(ENC_LAYERS):
+            call(ws["encoder"])
+        for _ in range(DEC_LAYERS):
+            call(ws["decoder"])
+
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        frame()
+        ts.append(time.perf_counter() - t0)
+    return statistics.median(ts), threads
+
+
+class CpuClip:
+    """The unmodified reference model on the host cores, through its own API only: one step = a fresh 2-frame mini clip
+    through ``GoMatching.batch_inference`` (spotting with MSDeformAttn via ms_deform_attn_core_pytorch -- BASELINE.json
+    configs[0] -- plus first-frame ID assignment and one short-term match)."""
+    FRAMES = 2
+
+    def __init__(self, args):
+        import torch
+        from tools.refhost import loader as L
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.threads = torch.get_num_threads()
+        self.L = L
+        self.model = L.build_gomatching(L.build_cfg(device="cpu"), seed=0)
+        self.inputs = L.frames_to_inputs(L.synthetic_clip(4, args.height, args.width, seed=1))
+        self.k = 0
+
+    def step(self):
+        """returns seconds for the step's FRAMES frames"""
+        import torch
+        inp = [self.inputs[(self.k + i) % len(self.inputs)] for i in range(self.FRAMES)]
+        self.k += 1
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            self.model.batch_inference(inp, 0, 0, [], self.L.new_time_cost())
+        return time.perf_counter() - t0
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" = one frame's 1 enc + 1 dec call on the host, scaled to the frame's 6 + 6 calls
-    import torch  # noqa: F401
-    per_frame = []
-    threads = 1
-    for i in range(args.warmup + args.steps):
-        s, te, td, threads = cpu_reference_frame_seconds(1, args.dist)
-        if i >= args.warmup:
-            per_frame.append(s)
-    sec = sum(per_frame) / len(per_frame)
+    workload = resolve_workload(args)
+    if workload == "clip":
+        cpu = CpuClip(args)
+        for _ in range(args.warmup):
+            cpu.step()
+        secs = [cpu.step() for _ in range(args.steps)]
+        sec = sum(secs) / len(secs) / cpu.FRAMES
+        threads, kind, fps_step = cpu.threads, "reference", cpu.FRAMES
+        sample = ("per step: a fresh %d-frame %dx%d mini clip through the unmodified reference GoMatching.batch_inference on "
+                  "the host (spotting with MSDeformAttn via ms_deform_attn_core_pytorch + ID assignment / short-term "
+                  "match), %d threads" % (cpu.FRAMES, args.width, args.height, threads))
+        cfg, metric = clip_config(args), "frames/sec (DeepSolo+LST, %dx%d)" % (args.width, args.height)
+    else:
+        secs = []
+        for i in range(args.warmup + args.steps):
+            s, threads = cpu_op_frame_seconds(1, args.dist)
+            if i >= args.warmup:
+                secs.append(s)
+        sec = sum(secs) / len(secs)
+        kind, fps_step = "port", 1
+        sample = ("per step: all 6 encoder (Lq=S=19160) + 6 decoder (Lq=2500) MSDeformAttn calls of one 1280x720 frame via "
+                  "F.grid_sample (oracle.core_gridsample = ms_deform_attn_core_pytorch restated), %d threads" % threads)
+        cfg, metric = op_config(args), "frames/sec (MSDeformAttn hot path)"
     val = 1.0 / sec
-    sample = ("per step: 1 encoder (Lq=S=19160) + 1 decoder (Lq=2500) MSDeformAttn call of one 1280x720 frame via "
-              "F.grid_sample, scaled x6 each")
     line = {
-        "impl": "reference", "metric": "frames/sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * fps_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "frames_per_step": fps_step,
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-def workload_config(args, frames):
-    return {
-        "workload": "MSDeformAttn hot path per 1280x720 DeepSolo-R50 frame: 6 encoder self-attn (Lq=S=19160, 4 levels "
-                    "90x160..12x20) + 6 point-query decoder cross-attn (Lq=100x25) forwards, d=256, 8 heads, 4 points",
-        "frames_per_step_per_gpu": frames, "sampling_distribution": args.dist,
-        "fused_glue": not args.unfused,
-        "l2": "inputs larger than L2 (549 MB per encoder launch, 208 MB per decoder launch; buffer sets rotate)",
-        "parallelism": "frames sharded across GPUs (dp%d); no collective inside the op, one NCCL gather of the "
-                       "per-frame records to the tracker rank per step when N > 1" % args.gpus,
-    }
+def resolve_workload(args):
+    if args.workload == "auto":
+        return "clip" if clip_available() else "op"
+    if args.workload == "clip" and not clip_available():
+        raise SystemExit("bench.py: --workload clip needs the reference's Python (run __graft_entry__.build() in the "
+                         "build container to stage baseline/_ref)")
+    return args.workload
 
 
 # ---------------------------------------------------------------------------------------------------
-# device workload
+# op workload
 # ---------------------------------------------------------------------------------------------------
-def device_workload(kind, frames, seed, dist, device):
+def device_workload(kind, frames, seed, dist, device, height=None, width=None, proposals=100):
     """One buffer set for a batch of `frames` frames, generated on the device with a seeded generator
     (reference points come from the CPU generator of gomatching_b200.synthetic)."""
     import torch
     from gomatching_b200 import synthetic as syn
     g = torch.Generator(device=device).manual_seed(seed)
-    shapes_l = syn.level_shapes(HEIGHT, WIDTH, L)
+    shapes_l = syn.level_shapes(height or HEIGHT, width or WIDTH, L)
     shapes = torch.as_tensor(shapes_l, dtype=torch.long)
     S = int(shapes.prod(1).sum())
     if kind == "encoder":
         ref = syn.encoder_reference_points(shapes_l, 1).expand(frames, -1, -1, -1).contiguous()
     else:
-        ref = syn.decoder_reference_points(torch.Generator().manual_seed(seed), frames, 100, 25, L)
+        ref = syn.decoder_reference_points(torch.Generator().manual_seed(seed), frames, proposals, 25, L)
     Lq = ref.shape[1]
     ref = ref.to(device)
     wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float().to(device)
@@ -215,12 +293,303 @@ def device_workload(kind, frames, seed, dist, device):
             target = target * 0.0 + 0.5
         offsets = (target - ref[:, :, None, :, None, :]) * wh[None, None, None, :, None, :]
     return {"kind": kind, "value": value, "ref": ref, "offsets": offsets.contiguous(), "logits": logits,
-            "shapes": shapes.to(device), "lsi": syn.level_start_index(shapes_l).to(device), "Lq": Lq, "S": S}
+            "shapes": shapes.to(device), "lsi": syn.level_start_index(shapes_l).to(device), "Lq": Lq, "S": S,
+            "shapes_list": shapes_l}
 
 
 def algorithmic_bytes(frames, S, Lq):
     v = min(frames * S * M * D, 4 * frames * Lq * M * L * P * D) * 4
     return v + 12 * frames * Lq * M * L * P + 4 * frames * Lq * M * D
+
+
+def time_launches(fn, sets, reps, warm=2):
+    """Mean CUDA-event microseconds of fn(w) over `reps` passes of the rotating buffer sets (after `warm` passes)."""
+    import torch
+    for _ in range(warm):
+        for w in sets:
+            fn(w)
+    evs = []
+    for _ in range(reps):
+        for w in sets:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(w)
+            b.record()
+            evs.append((a, b))
+    torch.cuda.synchronize()
+    return 1e3 * sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+
+
+def run_op_workload(args, world, rank, device, steps, warmup, barrier, with_e2e):
+    import torch
+    import torch.distributed as dist
+    import gomatching_b200 as g
+    from gomatching_b200 import _native
+
+    F = args.frames or FRAMES_PER_STEP
+    tuning = None
+    if args.tuning:
+        tuning = {k: int(v) for k, v in (kv.split("=") for kv in args.tuning.split(","))}
+    enc = [device_workload("encoder", F, 100 + 7 * rank + i, args.dist, device) for i in range(ENC_LAYERS)]
+    dec = [device_workload("decoder", F, 200 + 7 * rank + i, args.dist, device) for i in range(DEC_LAYERS)]
+    if args.unfused:
+        for w in enc + dec:
+            w["loc"], w["attn"] = g.locations_softmax(w["shapes"], w["ref"], w["offsets"], w["logits"], 8)
+
+    def launch(w, tn=None):
+        if args.unfused:
+            return g.ms_deform_attn_forward(w["value"], w["shapes"], w["lsi"], w["loc"], w["attn"], 64, tuning=tn)
+        return g.ms_deform_attn_forward_fused(w["value"], w["shapes"], w["lsi"], w["ref"], w["offsets"], w["logits"],
+                                              tuning=tn, spatial_shapes_list=w["shapes_list"])
+
+    rec_block = None
+    if world > 1:
+        from gomatching_b200 import video as V
+        schema = V.RecordSchema(max_instances=100)
+        rec_block = torch.randint(0, 255, (F, schema.stride), dtype=torch.uint8, device=device)
+
+    enc_events = []
+
+    def step(record=False):
+        for w in enc:
+            if record:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            launch(w, tuning)
+            if record:
+                b.record()
+                enc_events.append((a, b))
+        for w in dec:
+            launch(w)
+        if rec_block is not None:
+            V.gather_records(rec_block, F * world, dst=0)
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    calls0 = _native.calls
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step(record=True)
+    t1.record()
+    barrier()
+    launches = _native.calls - calls0
+    ms_total = t0.elapsed_time(t1)
+    enc_ms = [a.elapsed_time(b) for a, b in enc_events]
+    if world > 1:
+        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / steps
+    res = {"value": world * F / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "frames_per_step_per_gpu": F,
+           "steps": steps, "launches": launches * world, "enc_mean_ms": sum(enc_ms) / len(enc_ms), "enc_launches": len(enc_ms),
+           "b_alg": algorithmic_bytes(F, enc[0]["S"], enc[0]["Lq"]), "S": enc[0]["S"], "Lq": enc[0]["Lq"], "F": F,
+           "fused_glue": not args.unfused, "e2e": None, "sublines": None}
+
+    if with_e2e:
+        keys = ("value", "ref", "offsets", "logits")
+        host_in = [{k: torch.empty(w[k].shape, dtype=w[k].dtype, pin_memory=True).copy_(w[k]) for k in keys}
+                   for w in enc + dec]
+        host_out = [torch.empty((F, w["Lq"], M * D), dtype=torch.float32, pin_memory=True) for w in enc + dec]
+        h2d = sum(t.numel() * t.element_size() for h in host_in for t in h.values())
+        d2h = sum(t.numel() * t.element_size() for t in host_out)
+        copy_stream = torch.cuda.Stream()
+
+        def e2e_step():
+            cur = torch.cuda.current_stream()
+            staged = []
+            for w, h in zip(enc + dec, host_in):
+                with torch.cuda.stream(copy_stream):
+                    d = {k: h[k].to(device, non_blocking=True) for k in keys}
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                staged.append((w, d, ev))
+            for (w, d, ev), ho in zip(staged, host_out):
+                cur.wait_event(ev)
+                o = g.ms_deform_attn_forward_fused(d["value"], w["shapes"], w["lsi"], d["ref"], d["offsets"], d["logits"],
+                                                   spatial_shapes_list=w["shapes_list"])
+                for t in d.values():
+                    t.record_stream(cur)
+                ho.copy_(o, non_blocking=True)
+            cur.synchronize()
+
+        e2e_steps = max(3, min(steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - w0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        res["e2e"] = {"value": world * F / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                      "api": "gomatching_b200.ms_deform_attn_forward_fused on pinned host tensors (H2D on a copy stream, "
+                             "D2H of every output): intermediate activations cross PCIe, which the clip workload avoids"}
+        del host_in, host_out
+
+    # ---- sub-lines (rank 0, N = 1 only): F = 1, bf16 storage, the 1080p shape (config 5), the reference kernel ---------
+    if rank == 0 and world == 1 and not args.no_sublines:
+        sub = {}
+        peak = _peak()[0]
+
+        def line(us, frames, S, Lq, esize=4):
+            v = min(frames * S * M * D, 4 * frames * Lq * M * L * P * D) * esize
+            b = v + 12 * frames * Lq * M * L * P + esize * frames * Lq * M * D
+            return {"us_per_launch": us, "frames_per_launch": frames, "GBps": b / us / 1e3, "frac": b / us / 1e3 / peak}
+
+        dec_us = time_launches(lambda w: launch(w), dec, 3)
+        sub["decoder_f32_F%d" % F] = line(dec_us, F, dec[0]["S"], dec[0]["Lq"])
+        del enc[2:], dec[2:]
+        torch.cuda.empty_cache()
+        e1 = [device_workload("encoder", 1, 300 + i, args.dist, device) for i in range(8)]
+        sub["encoder_f32_F1"] = line(time_launches(lambda w: launch(w), e1, 5), 1, e1[0]["S"], e1[0]["Lq"])
+        d1 = [device_workload("decoder", 1, 320 + i, args.dist, device) for i in range(8)]
+        sub["decoder_f32_F1"] = line(time_launches(lambda w: launch(w), d1, 5), 1, d1[0]["S"], d1[0]["Lq"])
+        del e1, d1
+        for w in enc + dec:
+            w["value"] = w["value"].bfloat16()
+        sub["encoder_bf16_F%d" % F] = line(time_launches(lambda w: launch(w), enc, 5), F, enc[0]["S"], enc[0]["Lq"], 2)
+        sub["decoder_bf16_F%d" % F] = line(time_launches(lambda w: launch(w), dec, 5), F, dec[0]["S"], dec[0]["Lq"], 2)
+        del enc[:], dec[:]
+        torch.cuda.empty_cache()
+        big = [device_workload("encoder", 4, 400 + i, args.dist, device, 1080, 1920) for i in range(3)]
+        sub["encoder_f32_1080p_F4"] = line(time_launches(lambda w: launch(w), big, 3), 4, big[0]["S"], big[0]["Lq"])
+        bigd = [device_workload("decoder", 4, 420 + i, args.dist, device, 1080, 1920, proposals=300) for i in range(3)]
+        sub["decoder_f32_1080p_F4_300q"] = line(time_launches(lambda w: launch(w), bigd, 3), 4, bigd[0]["S"], bigd[0]["Lq"])
+        del big, bigd
+        torch.cuda.empty_cache()
+        res["sublines"] = sub
+    return res
+
+
+def reference_cuda_kernel_us(device, dist_name, F):
+    """The UNMODIFIED reference CUDA kernel rebuilt for sm_100a (oracle/_ref/libmsda_refcuda.so), same encoder-shape
+    launch, same protocol -- the "kernel to beat".  Baseline leg only; None when the library was not built."""
+    import ctypes
+    import torch
+    import gomatching_b200 as g
+    path = os.path.join(ROOT, "oracle", "_ref", "libmsda_refcuda.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    lib.refcuda_msda_forward_f32.restype = ctypes.c_int
+    lib.refcuda_msda_forward_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 7 + [ctypes.c_void_p] * 2
+    sets = [device_workload("encoder", F, 500 + i, dist_name, device) for i in range(3)]
+    for w in sets:
+        w["loc"], w["attn"] = g.locations_softmax(w["shapes"], w["ref"], w["offsets"], w["logits"], 8)
+        w["out"] = torch.empty(F, w["Lq"], M * D, device=device)
+
+    def fn(w):
+        rc = lib.refcuda_msda_forward_f32(w["value"].data_ptr(), w["shapes"].data_ptr(), w["lsi"].data_ptr(),
+                                          w["loc"].data_ptr(), w["attn"].data_ptr(), F, w["S"], M, D, L, w["Lq"], P,
+                                          w["out"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+    return time_launches(fn, sets, 3, warm=1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clip workload
+# ---------------------------------------------------------------------------------------------------
+def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
+    import torch
+    import torch.distributed as dist
+    from gomatching_b200 import _native
+    from gomatching_b200.video.tracking import ClipTracker, round_plan
+    from tools.refhost import loader as Lr
+
+    F = args.frames or 4
+    w0 = F if (args.tracker_frames < 0 or world == 1) else args.tracker_frames
+    weights = [w0] + [F] * (world - 1)
+    per_step = sum(weights)
+    cfg = Lr.build_cfg(device=str(device))
+    model = Lr.build_gomatching(cfg, seed=0, b200=args.level)
+    pool_n = 8
+    clip = Lr.synthetic_clip(pool_n, args.height, args.width, seed=11 + rank)
+    host_pool = [torch.from_numpy(f).pin_memory() for f in clip]
+    dev_pool = [f.to(device) for f in host_pool]
+    plan = round_plan(per_step, weights)[0]
+    mine = [(t, s) for t, r, s in plan if r == rank]
+
+    def reduce_max(x):
+        if world > 1:
+            t = torch.tensor([x], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def run(pool, n_steps, associate=True, host_results=False):
+        """n_steps rounds after `warmup` untimed ones; returns (ms per step by CUDA events incl. the association tail,
+        tracker, kernel event log, C-ABI calls)."""
+        ct = ClipTracker(model, weights=weights, overlap=True, associate=associate, host_results=host_results)
+        k = [0]
+
+        def one_round():
+            frames = [None] * per_step
+            for t, s in mine:
+                frames[t] = pool[(k[0] * F + s) % pool_n]
+            k[0] += 1
+            ct.feed(frames)
+
+        for _ in range(max(warmup, 3)):
+            one_round()
+        ct.flush()
+        barrier()
+        log = []
+        _native.event_log = log
+        calls0 = _native.calls
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0 = ct.association_seconds()
+        t0.record()
+        for _ in range(n_steps):
+            one_round()
+        ct.flush()                      # the last rounds' association is inside the timed region
+        t1.record()
+        barrier()
+        _native.event_log = None
+        ms = reduce_max(t0.elapsed_time(t1) / n_steps)
+        info = {"calls": _native.calls - calls0, "assoc_ms_per_frame": (ct.association_seconds() - a0) * 1e3 / (n_steps * per_step),
+                "spot_ms_per_frame": None, "d2h": sum(t.numel() * t.element_size() for t in ct.host_ids[-n_steps * per_step:]) / n_steps
+                if host_results and rank == 0 else 0}
+        ct.drain()
+        return ms, info, log
+
+    ms, info, log = run(dev_pool, steps)
+    res = {"value": per_step / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": per_step, "weights": weights,
+           "launches": info["calls"] * world, "assoc_ms_per_frame": info["assoc_ms_per_frame"], "level": args.level}
+    enc_us = [a.elapsed_time(b) * 1e3 for tag, a, b in log if tag[3] == tag[2]]       # Lq == S: encoder self-attention
+    dec_us = [a.elapsed_time(b) * 1e3 for tag, a, b in log if tag[3] != tag[2]]
+    if enc_us:
+        S = log[0][0][2]
+        res["in_pipeline"] = {"encoder_us": statistics.mean(enc_us), "decoder_us": statistics.mean(dec_us) if dec_us else None,
+                              "encoder_launches": len(enc_us), "S": S, "b_alg": algorithmic_bytes(1, S, S)}
+    if not args.no_e2e:
+        ms_e, info_e, _ = run(host_pool, max(3, steps // 2), host_results=True)
+        frame_bytes = host_pool[0].numel()
+        res["e2e"] = {"value": per_step / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_step,
+                      "d2h_bytes_per_step": int(info_e["d2h"]), "ms_per_step": ms_e, "steps": max(3, steps // 2),
+                      "api": "gomatching_b200.video.ClipTracker.feed(pinned uint8 HWC frames) -> per-frame track ids on the "
+                             "host (frame H2D, frame-batcher kernel, spotter, record gather, reference tracker, ids D2H)"}
+    ms_s, _, _ = run(dev_pool, max(3, steps // 2), associate=False)
+    res["spotting_only"] = {"value": per_step / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
+                            "note": "same loop, records gathered, association skipped: the part that shards"}
+    return res
+
+
+def _peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if "hbm_gbs" in peaks:
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "6650 GB/s (of fallback, B200_PROFILING.md)"
 
 
 _JSON_OUT = sys.stdout
@@ -234,7 +603,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import gomatching_b200 as g
     from gomatching_b200 import _native
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,177 +616,112 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     _native.lib()
-
-    F = args.frames
-    tuning = None
-    if args.tuning:
-        tuning = {k: int(v) for k, v in (kv.split("=") for kv in args.tuning.split(","))}
-
-    # one buffer set per layer so consecutive launches never touch the same bytes
-    enc = [device_workload("encoder", F, 100 + 7 * rank + i, args.dist, device) for i in range(ENC_LAYERS)]
-    dec = [device_workload("decoder", F, 200 + 7 * rank + i, args.dist, device) for i in range(DEC_LAYERS)]
-    if args.unfused:
-        for w in enc + dec:
-            w["loc"], w["attn"] = g.locations_softmax(w["shapes"], w["ref"], w["offsets"], w["logits"], 8)
-
-    def launch(w, tn=None):
-        if args.unfused:
-            return g.ms_deform_attn_forward(w["value"], w["shapes"], w["lsi"], w["loc"], w["attn"], 64, tuning=tn)
-        return g.ms_deform_attn_forward_fused(w["value"], w["shapes"], w["lsi"], w["ref"], w["offsets"], w["logits"],
-                                              tuning=tn)
-
-    # N > 1: the path's one exchange step -- per-step gather of this rank's frame records (query embeddings and
-    # rescored detections, 0.49 MB per frame at 100 queries) to the tracker rank over NCCL / NVLink
-    rec_block = None
-    if world > 1:
-        from gomatching_b200 import video as V
-        schema = V.RecordSchema(max_instances=100)
-        rec_block = torch.randint(0, 255, (F, schema.stride), dtype=torch.uint8, device=device)
-
-    enc_events = []
-
-    def step(record=False):
-        outs = []
-        for w in enc:
-            if record:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-            outs.append(launch(w, tuning))
-            if record:
-                b.record()
-                enc_events.append((a, b))
-        for w in dec:
-            outs.append(launch(w))
-        if rec_block is not None:
-            V.gather_records(rec_block, F * world, dst=0)
-        return outs
+    workload = resolve_workload(args)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for _ in range(args.steps):
-        step(record=True)
-    t1.record()
-    barrier()
-    ms_total = t0.elapsed_time(t1)
-    enc_ms = [a.elapsed_time(b) for a, b in enc_events]
+    clip = None
+    if workload == "clip":
+        clip = run_clip_workload(args, world, rank, device, args.steps, args.warmup, barrier)
+        op_steps = max(3, min(args.steps, 5))
+        op = run_op_workload(args, world, rank, device, op_steps, 3, barrier, with_e2e=False)
+    else:
+        op = run_op_workload(args, world, rank, device, args.steps, args.warmup, barrier, with_e2e=not args.no_e2e)
     clocks = sampler.stop() if rank == 0 else None
-
-    if world > 1:
-        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = world * F / (ms_per_step * 1e-3)
-
-    # ---- e2e: host buffers in, host buffers out, copies inside the timed region -------------------------
-    e2e = None
-    if not args.no_e2e:
-        keys = ("value", "ref", "offsets", "logits")
-        host_in = [{k: torch.empty(w[k].shape, dtype=w[k].dtype, pin_memory=True).copy_(w[k]) for k in keys}
-                   for w in enc + dec]
-        host_out = [torch.empty((F, w["Lq"], M * D), dtype=torch.float32, pin_memory=True) for w in enc + dec]
-        h2d = sum(t.numel() * t.element_size() for h in host_in for t in h.values())
-        d2h = sum(t.numel() * t.element_size() for t in host_out)
-        copy_stream = torch.cuda.Stream()
-
-        def e2e_step():
-            # copies for launch i+1 overlap the kernel of launch i (copy stream + events); results go back on the
-            # compute stream's tail so every output byte reaches the host inside the step
-            cur = torch.cuda.current_stream()
-            staged = []
-            for w, h in zip(enc + dec, host_in):
-                with torch.cuda.stream(copy_stream):
-                    d = {k: h[k].to(device, non_blocking=True) for k in keys}
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                staged.append((w, d, ev))
-            for (w, d, ev), ho in zip(staged, host_out):
-                cur.wait_event(ev)
-                o = g.ms_deform_attn_forward_fused(d["value"], w["shapes"], w["lsi"], d["ref"], d["offsets"], d["logits"])
-                for t in d.values():
-                    t.record_stream(cur)
-                ho.copy_(o, non_blocking=True)
-            cur.synchronize()
-
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - w0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": world * F / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "api": "gomatching_b200.ms_deform_attn_forward_fused on pinned host tensors (H2D on a copy stream, D2H of every output)"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    b_alg = algorithmic_bytes(F, enc[0]["S"], enc[0]["Lq"])
-    enc_mean_ms = sum(enc_ms) / len(enc_ms)
-    achieved = b_alg / (enc_mean_ms * 1e-3) / 1e9
+    peak, peak_src = _peak()
+    achieved = op["b_alg"] / (op["enc_mean_ms"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "msda_fwd_fast_kernel<float,32,...,FUSED> encoder launch (N=%d, Lq=S=%d)" % (F, enc[0]["S"]),
-                "algorithmic_bytes_per_launch": b_alg, "mean_launch_us": enc_mean_ms * 1e3,
-                "launches_timed": len(enc_ms), "peak_source": peak_src,
-                "gather_bytes_per_launch": 4 * F * enc[0]["Lq"] * M * L * P * D * 4}
-    # secondary bound: the SM's L1 data pipe returns at most one 128-byte row per clock per SM
+                "traffic": None, "target_frac": 0.60,
+                "kernel": "encoder-shape sampler launch (N=%d, Lq=S=%d), fused glue" % (op["F"], op["S"]),
+                "algorithmic_bytes_per_launch": op["b_alg"], "mean_launch_us": op["enc_mean_ms"] * 1e3,
+                "launches_timed": op["enc_launches"], "peak_source": peak_src,
+                "gather_bytes_per_launch": 4 * op["F"] * op["Lq"] * M * L * P * D * 4}
     if clocks and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(device).multi_processor_count
-        rows = 4 * F * enc[0]["Lq"] * M * L * P
+        rows = 4 * op["F"] * op["Lq"] * M * L * P
         roofline["l1_pipe"] = {"bound": "l1 data pipe (1 row/clk/SM)", "unit": "rows/clk/SM", "peak": 1.0,
-                               "achieved": rows / (enc_mean_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sms)}
+                               "achieved": rows / (op["enc_mean_ms"] * 1e-3 * clocks["sm_mhz"] * 1e6 * sms)}
+    if clip and clip.get("in_pipeline"):
+        ip = clip["in_pipeline"]
+        ip["GBps"] = ip["b_alg"] / ip["encoder_us"] / 1e3
+        ip["frac"] = ip["GBps"] / peak
+        ip["note"] = "same kernel timed live inside the clip's model forward: N=1, value just written by value_proj (L2-warm)"
+        roofline["in_pipeline"] = ip
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             tr = json.load(open(traffic_file))
-            roofline["traffic"] = tr.get("encoder_dram_bytes_per_launch_at_frames", {}).get(str(F))
+            roofline["traffic"] = tr.get("encoder_dram_bytes_per_launch_at_frames", {}).get(str(op["F"]))
             roofline["traffic_source"] = tr.get("source")
         except Exception:
             pass
 
     cpu = None
+    ref_kernel = None
     if not args.no_cpu_baseline:
-        sec, te, td, threads = cpu_reference_frame_seconds(5, args.dist)
-        cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "median of 5: 1 encoder (%.3f s) + 1 decoder (%.3f s) call of one frame via F.grid_sample "
-                         "(oracle.core_gridsample = ms_deform_attn_core_pytorch restated), scaled x6 each" % (te, td)}
+        if workload == "clip":
+            c = CpuClip(args)
+            c.step()
+            secs = [c.step() for _ in range(2)]
+            sec = statistics.median(secs) / c.FRAMES
+            cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": c.threads, "kind": "reference",
+                   "sample": "2 steps after 1 warm-up, each a fresh %d-frame %dx%d mini clip through the unmodified reference "
+                             "GoMatching.batch_inference on the host (MSDeformAttn via ms_deform_attn_core_pytorch)"
+                             % (c.FRAMES, args.width, args.height)}
+            del c
+        else:
+            sec, threads = cpu_op_frame_seconds(3, args.dist)
+            cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": threads, "kind": "port",
+                   "sample": "median of 3: all 6 encoder + 6 decoder calls of one frame via F.grid_sample "
+                             "(oracle.core_gridsample = ms_deform_attn_core_pytorch restated)"}
+        if world == 1 and not args.no_sublines:
+            us = reference_cuda_kernel_us(device, args.dist, op["F"])
+            if us is not None:
+                ref_kernel = {"ref_cuda_kernel_us": us, "b200_kernel_us": op["enc_mean_ms"] * 1e3,
+                              "speedup": us / (op["enc_mean_ms"] * 1e3),
+                              "note": "unmodified reference kernel rebuilt for sm_100a (core op; loc/attn precomputed), same "
+                                      "encoder-shape launch and protocol; the B200 time includes the fused glue"}
 
-    line = {
-        "metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, generated on device)",
-        "config": workload_config(args, F), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": world * args.steps * (ENC_LAYERS + DEC_LAYERS), "roofline": roofline, "cpu_baseline": cpu,
-        "msda_hbm_gbs": achieved,
-    }
+    msda = {"metric": "frames/sec (MSDeformAttn hot path only)", "value": op["value"], "unit": "frames/s",
+            "ms_per_step": op["ms_per_step"], "frames_per_step_per_gpu": op["frames_per_step_per_gpu"], "steps": op["steps"],
+            "msda_hbm_gbs": achieved, "fused_glue": op["fused_glue"], "sublines": op["sublines"], "reference_kernel": ref_kernel,
+            "config": op_config(args)}
+    if workload == "clip":
+        line = {
+            "metric": "frames/sec (DeepSolo+LST, %dx%d)" % (args.width, args.height), "value": clip["value"], "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": clip["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded uint8 frames; reference initialisers, seeded)", "config": clip_config(args),
+            "frames_per_step": clip["frames_per_step"], "round_weights": clip["weights"], "install_level": clip["level"],
+            "parallelism": "frames sharded across GPUs (dp%d), N=1 per forward; one NCCL gather of the round's records to "
+                           "rank 0; the reference's tracker on rank 0 in a worker thread" % world,
+            "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "spotting_only": clip["spotting_only"],
+            "clocks": clocks, "e2e": clip.get("e2e"), "gpu_launches": clip["launches"],
+            "gpu_launches_note": "kernel-launching C-ABI calls of libmsda_b200.so in the timed region, all ranks (each "
+                                 "enqueues >= 1 kernel); cuDNN / cuBLAS kernels of the reference's eager code not counted",
+            "roofline": roofline, "cpu_baseline": cpu, "msda": msda, "msda_hbm_gbs": achieved,
+        }
+    else:
+        line = {
+            "metric": "frames/sec (MSDeformAttn hot path)", "value": op["value"], "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": op["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, generated on device)",
+            "config": op_config(args), "frames_per_step": op["frames_per_step_per_gpu"] * world, "clocks": clocks,
+            "e2e": op["e2e"], "gpu_launches": op["launches"], "roofline": roofline, "cpu_baseline": cpu, "msda": msda,
+            "msda_hbm_gbs": achieved,
+        }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

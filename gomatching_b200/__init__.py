@@ -25,18 +25,24 @@ __all__ = [
 ]
 
 
-def install_into_adet():
+def install_into_adet(level: str = "layers"):
     """Bind this implementation where the reference looks its operator up.
 
-    * ``adet._C.ms_deform_attn_forward/backward``  (csrc/vision.cpp:52-55) -> the C-ABI kernels
-    * ``adet.layers.ms_deform_attn.MSDeformAttn`` and ``adet.layers.deformable_transformer.MSDeformAttn``
-      (deformable_transformer.py:16) -> :class:`MSDeformAttn`
-    * ``adet.layers.deformable_transformer.DeformableTransformerEncoderLayer`` (:218) -> the drop-in layer
-    Call after ``adet`` is importable; modules that are not imported yet are skipped.
-    """
+    ``level`` selects how much is swapped (each level includes the previous one):
+      "op"      ``adet._C.ms_deform_attn_forward/backward`` (csrc/vision.cpp:52-55) -> the C-ABI kernels.  Bit-identical
+                to the reference CUDA kernel, so every downstream tensor -- and every track ID -- is unchanged.
+      "module"  ``adet.layers.ms_deform_attn.MSDeformAttn`` and ``adet.layers.deformable_transformer.MSDeformAttn``
+                (deformable_transformer.py:16) -> :class:`MSDeformAttn` (fused glue, tensor-core projections;
+                within 1e-4 of the reference module).
+      "layers"  ``adet.layers.deformable_transformer.DeformableTransformerEncoderLayer`` (:218) and
+                ``DeformableCompositeTransformerDecoderLayer`` (:326) -> the drop-in layers (default).
+    Call after ``adet`` is importable and BEFORE the model is constructed; modules that are not imported yet are
+    skipped."""
     import sys
     import types
 
+    if level not in ("op", "module", "layers"):
+        raise ValueError("level must be 'op', 'module' or 'layers', got %r" % (level,))
     c = sys.modules.get("adet._C")
     if c is None:
         c = types.ModuleType("adet._C")
@@ -45,10 +51,14 @@ def install_into_adet():
             sys.modules["adet"]._C = c
     c.ms_deform_attn_forward = ms_deform_attn_forward
     c.ms_deform_attn_backward = ms_deform_attn_backward
+    if level == "op":
+        return c
     for name in ("adet.layers.ms_deform_attn", "adet.layers.deformable_transformer", "adet.layers"):
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "MSDeformAttn"):
             mod.MSDeformAttn = MSDeformAttn
+        if level != "layers":
+            continue
         if mod is not None and hasattr(mod, "DeformableTransformerEncoderLayer"):
             mod.DeformableTransformerEncoderLayer = DeformableTransformerEncoderLayer
         if mod is not None and hasattr(mod, "DeformableCompositeTransformerDecoderLayer"):

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmsda_b200.so")
 _lock = threading.Lock()
 _lib = None
+ABI_VERSION = 2      # include/msda_b200.h MSDA_B200_ABI_VERSION; bumped whenever the exported symbol list changes
 
 # every symbol include/msda_b200.h declares; tests/test_abi.py checks header <-> list <-> .so agree
 SYMBOLS = (
@@ -39,6 +40,7 @@ SYMBOLS = (
     "msda_b200_frames_u8_to_chw_f32",
     "msda_b200_staged_set_host_shapes",
     "msda_b200_add_layernorm_f32",
+    "msda_b200_shape_mismatch_epoch",
 )
 
 
@@ -63,16 +65,19 @@ class MSDAError(RuntimeError):
 
 
 def lib() -> ctypes.CDLL:
-    """Load the CUDA library.  Builds it first if nvcc is available and the .so is stale or absent."""
+    """Load the CUDA library.  Builds it first if it is absent, or stale and nvcc is available (``build.build()`` is a
+    no-op on a fresh library and serialises concurrent builders -- one rank per GPU -- with a file lock)."""
     global _lib
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is not None:
             return _lib
+        from . import build as _build
         if not os.path.exists(LIB_PATH) or os.environ.get("MSDA_B200_REBUILD") == "1":
-            from . import build as _build
-            _build.build()
+            _build.build(force=os.environ.get("MSDA_B200_REBUILD") == "1")
+        elif _build.have_nvcc():
+            _build.build()                              # rebuilds only if a source is newer than the library
         if not os.path.exists(LIB_PATH):
             raise MSDAError("libmsda_b200.so is missing and could not be built; there is no CPU/PyTorch fallback")
         L = ctypes.CDLL(LIB_PATH)
@@ -123,13 +128,26 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_staged_set_host_shapes.argtypes = [vp, vp, ci]
         L.msda_b200_frames_u8_to_chw_f32.restype = ci
         L.msda_b200_frames_u8_to_chw_f32.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp]
-        if L.msda_b200_abi_version() != 1:
-            raise MSDAError("libmsda_b200.so ABI version mismatch")
+        L.msda_b200_shape_mismatch_epoch.restype = ci
+        L.msda_b200_shape_mismatch_epoch.argtypes = []
+        if L.msda_b200_abi_version() != ABI_VERSION:
+            raise MSDAError("libmsda_b200.so ABI version %d, expected %d (stale library: rebuild with "
+                            "python -m gomatching_b200.build --force)" % (L.msda_b200_abi_version(), ABI_VERSION))
         _lib = L
     return _lib
 
 
+# Measurement hooks (bench.py): ``calls`` counts the kernel-launching C-ABI calls made through this module (every one
+# of them goes through ``check``; each enqueues at least one of this library's kernels); ``event_log``, when set to a
+# list, makes the sampler entry points bracket their launch with CUDA events on the launching stream and append
+# ``(tag, start_event, stop_event)`` -- how bench.py times the sampler live inside the model's forward.
+calls = 0
+event_log = None
+
+
 def check(rc: int, what: str = "msda_b200") -> None:
+    global calls
+    calls += 1
     if rc != 0:
         msg = lib().msda_b200_error_string(int(rc))
         raise MSDAError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
@@ -159,6 +177,76 @@ def staged_shape_hint(spatial_shapes, level_start_index) -> None:
     lib().msda_b200_staged_set_host_shapes(sh.data_ptr(), ls.data_ptr(), int(ls.numel()))
 
 
+# ---- host-side level geometry for the TMA window kernel, keyed by VALUE ------------------------------------------------
+# The operator API hands over spatial_shapes / level_start_index as device tensors, and the reference builds fresh ones
+# for every frame (deformable_transformer.py:169), so an identity-keyed cache would pay a device->host read per frame.
+# Here the key is what identifies a pyramid cheaply on the host -- (device, S, L) -- and the entry is learned with ONE
+# device->host read the first time the key is seen (the reference's own `assert` at ms_deform_attn.py:131 pays such a
+# sync on every call).  Two pyramids can share S (portrait vs landscape), so every launch validates the entry against
+# the device tensors in-kernel (csrc/msda_forward_pipelined.cu shape guard): a wrong entry costs speed, never
+# correctness, and the mismatch epoch the kernels leave in pinned host memory drops the cache on a later call.
+_window_geometry = {}
+_window_seen_epoch = 0
+window_stats = {"learned": 0, "dropped": 0, "from_list": 0}
+
+
+def window_geometry(spatial_shapes, level_start_index, S: int, L: int, shapes_list=None) -> bool:
+    """Set the calling thread's window-kernel geometry hint for this pyramid.  False if it is not known and cannot be
+    learned right now (CUDA graph capture in progress): the caller then keeps the register-gather kernel."""
+    global _window_seen_epoch
+    import torch
+    L_ = lib()
+    ep = int(L_.msda_b200_shape_mismatch_epoch())
+    if ep != _window_seen_epoch:
+        _window_seen_epoch = ep
+        window_stats["dropped"] += len(_window_geometry)
+        _window_geometry.clear()
+    dev = spatial_shapes.device.index if spatial_shapes.is_cuda else -1
+    key = (dev, int(S), int(L))
+    hit = _window_geometry.get(key)
+    if shapes_list is not None:
+        flat = [int(v) for hw in shapes_list for v in hw]
+        if hit is None or hit[2] != flat:
+            sh = torch.tensor(flat, dtype=torch.int64).view(-1, 2)
+            if sh.shape[0] != L or int(sh.prod(1).sum()) != S:
+                raise ValueError("spatial_shapes_list %r does not describe %d levels with %d pixels" % (shapes_list, L, S))
+            ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1])).contiguous()
+            hit = _window_geometry[key] = (sh.contiguous(), ls, flat)
+            window_stats["from_list"] += 1
+    elif hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            return False
+        sh = spatial_shapes.detach().to("cpu", copy=True).to(dtype=torch.int64).contiguous()
+        ls = level_start_index.detach().to("cpu", copy=True).to(dtype=torch.int64).contiguous()
+        if len(_window_geometry) > 256:
+            _window_geometry.clear()
+        hit = _window_geometry[key] = (sh, ls, [int(v) for v in sh.flatten()])
+        window_stats["learned"] += 1
+    L_.msda_b200_staged_set_host_shapes(hit[0].data_ptr(), hit[1].data_ptr(), int(hit[1].numel()))
+    return True
+
+
+def auto_window_tuning(value, spatial_shapes, level_start_index, Lq: int, tuning, shapes_list=None):
+    """The launch plan for one sampler call.  An explicit ``tuning`` wins (modes 4 / 5 get their geometry hint here);
+    without one, fp32 encoder self-attention at the DeepSolo shape (Lq == S, D = 32, L = 4, P = 4) runs the TMA
+    window kernel (mode 5) whenever the pyramid's geometry is known on the host."""
+    import torch
+    N, S, M, D = value.shape
+    L = int(spatial_shapes.shape[0])
+    mode = tuning_mode(tuning)
+    if tuning is not None:
+        if mode in (4, 5):
+            if shapes_list is not None or os.environ.get("MSDA_B200_IDENTITY_HINT") != "1":
+                window_geometry(spatial_shapes, level_start_index, S, L, shapes_list)
+            else:
+                staged_shape_hint(spatial_shapes, level_start_index)
+        return tuning
+    if (value.dtype == torch.float32 and Lq == S and D == 32 and L == 4 and os.environ.get("MSDA_B200_NO_WINDOW") != "1"
+            and window_geometry(spatial_shapes, level_start_index, S, L, shapes_list)):
+        return _MODE5
+    return None
+
+
 def tuning_mode(tuning) -> int:
     if tuning is None:
         return 0
@@ -180,3 +268,6 @@ def make_tuning(tuning) -> "ctypes.POINTER(Tuning) | None":
         else:
             setattr(t, k, int(v))
     return ctypes.pointer(t)
+
+
+_MODE5 = {"mode": 5}

@@ -26,24 +26,55 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = os.path.join(HERE, "libmsda_b200.srchash")
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in sorted(os.path.join(CSRC, s) for s in SOURCES + HEADERS):
+        if os.path.exists(d):
+            with open(d, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
+
+
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """No-op when the library is newer than every source.  Concurrent callers (one rank per GPU on a fresh checkout)
+    are serialised by a file lock, and objects / the link output go to per-process temporaries before one atomic rename."""
     if not force and not _stale():
         return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():               # another process built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libmsda_b200.so cannot be built (there is no CPU fallback)")
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        o = os.path.join(CSRC, s.replace(".cu", ".%d.o" % os.getpid()))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -56,12 +87,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (s, out))
-    tmp = LIB + ".tmp"
+    tmp = LIB + ".%d.tmp" % os.getpid()
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
     os.replace(tmp, LIB)
+    with open(STAMP, "w") as f:
+        f.write(_source_hash() + "\n")
     for o in objs:
         try:
             os.remove(o)

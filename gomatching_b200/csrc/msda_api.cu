@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <new>
 
 #include "../../include/msda_b200.h"
@@ -133,7 +135,56 @@ int forward_common(const void* value, const int64_t* shapes, const int64_t* lsi,
 
 }  // namespace
 
+// ---- shape guard state: per device a ring of flag slots, one pinned host word for all devices ---------------------
+namespace msda {
+namespace {
+constexpr int kGuardSlots = 64, kGuardDevs = 64;
+std::mutex g_guard_mu;
+int* g_guard_ring[kGuardDevs] = {};
+int* g_guard_host = nullptr;          // pinned, mapped: the kernels store the epoch of a mismatch here
+std::atomic<int> g_guard_epoch{0};
+}  // namespace
+
+int shape_guard_acquire(int** flag, int** report, int* epoch, cudaStream_t stream) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= kGuardDevs) return MSDA_E_UNSUPPORTED;
+  if (!g_guard_ring[dev]) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return MSDA_E_UNSUPPORTED;                       // cannot allocate while a graph is being captured
+    }
+    std::lock_guard<std::mutex> lock(g_guard_mu);
+    if (!g_guard_host) {
+      e = cudaHostAlloc(reinterpret_cast<void**>(&g_guard_host), sizeof(int), cudaHostAllocPortable | cudaHostAllocMapped);
+      if (e != cudaSuccess) return (int)e;
+      *g_guard_host = 0;
+    }
+    if (!g_guard_ring[dev]) {
+      int* ring = nullptr;
+      e = cudaMalloc(reinterpret_cast<void**>(&ring), kGuardSlots * sizeof(int));
+      if (e != cudaSuccess) return (int)e;
+      e = cudaMemset(ring, 0, kGuardSlots * sizeof(int));
+      if (e != cudaSuccess) return (int)e;
+      g_guard_ring[dev] = ring;
+    }
+  }
+  int ep = g_guard_epoch.fetch_add(1) + 1;
+  if (ep <= 0) { g_guard_epoch = 1; ep = 1; }
+  *flag = g_guard_ring[dev] + (ep % kGuardSlots);
+  *report = g_guard_host;                              // portable + unified addressing: valid on every device
+  *epoch = ep;
+  return 0;
+}
+
+int shape_guard_last_mismatch() { return g_guard_host ? *reinterpret_cast<volatile int*>(g_guard_host) : 0; }
+}  // namespace msda
+
 extern "C" {
+
+int msda_b200_shape_mismatch_epoch(void) { return shape_guard_last_mismatch(); }
 
 int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
 

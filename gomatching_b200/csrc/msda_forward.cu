@@ -411,12 +411,11 @@ int launch_tiled(const FwdParams& p, cudaStream_t stream) {
   const int LP = LPT > 0 ? LPT : p.L * p.P;
   const size_t smem = (size_t)NW * LP * UPW * sizeof(float4);
   auto kern = msda_fwd_tiled_kernel<T, D, NW, UNROLL, LPT, MINB>;
-  static bool configured = false;   // attribute is per function; benign race (idempotent)
-  if (!configured) {
+  static PerDeviceOnce configured;   // function attributes are per device
+  if (configured.need()) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     // the gather lives on L1 hits: give L1 everything the records do not need
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 15);
-    configured = true;
   }
   if (smem > 64 * 1024) return MSDA_E_UNSUPPORTED;
   kern<<<p.grid, NW * 32, smem, stream>>>(p);
@@ -456,14 +455,17 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
     long long hw[4][2], lsi[4];
     if (sizeof(T) == 4 && staged_supported(p) && staged_get_host_shapes(hw, lsi)) {
       FwdParams lv0 = p;
-      lv0.grid = p.grid / 4;                              // one 17-warp CTA per SM
-      const int rc = launch_forward_pipelined_f32(lv0, hw, lsi, stream);
+      lv0.grid = p.grid / 4;                              // one 24-warp CTA per SM
+      int rc = shape_guard_acquire(&lv0.shape_flag, &lv0.shape_report, &lv0.shape_epoch, stream);
+      if (rc == 0) rc = launch_forward_pipelined_f32(lv0, hw, lsi, stream);
       if (rc != MSDA_E_UNSUPPORTED) {
         if (rc) return rc;
         FwdParams rest = p;                               // query levels 1..3: register-gather kernel
         rest.mode = kModeLinear;
         rest.q_level_begin = 1;
         rest.variant = 3;
+        rest.shape_flag = lv0.shape_flag;                 // ... or every query, if the host geometry was wrong
+        rest.shape_epoch = lv0.shape_epoch;
         return launch_forward_fast_f32(rest, stream);
       }
     }

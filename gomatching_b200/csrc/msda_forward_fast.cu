@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
   __syncthreads();
 
   const int cstride = M * D * EB;                   // bytes between horizontally adjacent pixels
-  const int q0 = (!pyramid && p.q_level_begin > 0) ? sStart[p.q_level_begin] : 0;   // first query of the range served
+  // first query of the range served; the whole range if the window kernel ahead of this launch reported a shape mismatch
+  const bool all_q = p.shape_flag != nullptr && *reinterpret_cast<const volatile int*>(p.shape_flag) == p.shape_epoch;
+  const int q0 = (!pyramid && p.q_level_begin > 0 && !all_q) ? sStart[p.q_level_begin] : 0;
   const int tiles_per_bm = pyramid ? sTileCum[NL] : (Lq - q0 + p.tile_q - 1) / p.tile_q;
   const long long total_tiles = (long long)p.N * tiles_per_bm * M;
   const int chunks_per_warp = (p.tile_q + NW * UPW - 1) / (NW * UPW);   // warp steps per tile
@@ -317,15 +319,14 @@ int launch_fast(const FwdParams& p, cudaStream_t stream) {
   constexpr int LPR = D / (VB / (int)sizeof(T)), UPW = 32 / LPR;
   const size_t smem = (size_t)NW * (REC16 ? 1 : 2) * LPT * UPW * sizeof(float4);
   auto kern = msda_fwd_fast_kernel<T, D, VB, LPT, PT, FUSED, NW, MINB, PD, REC16>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;   // function attributes are per device
+  if (configured.need()) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     // the gather lives on L1 hits: shared memory only holds the records.  Ask for just enough carve-out that MINB
     // CTAs fit (ncu: with too small a hint only ONE CTA was resident per SM).
     const int need_kb = (int)((MINB * (smem + 1024 + 256) + 1023) / 1024);
     int pct = (need_kb * 100 + 227) / 228 + 2;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-    configured = true;
   }
   kern<<<p.grid, NW * 32, smem, stream>>>(p);
   return (int)cudaGetLastError();

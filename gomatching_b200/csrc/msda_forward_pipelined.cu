@@ -79,9 +79,23 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
   __shared__ int sPart[2][kPlFrontMax][NL][3];
   __shared__ int sOrg[2][NL][2];      // per item parity, per sampled level: window origin (h0, w0) chosen by the producer
 
+  __shared__ int sMismatch;
   const int M = p.M, Lq = p.Lq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 2 * kPlFrontMax * NL * 3) (&sPart[0][0][0][0])[tid] = 0;
+  if (tid == 0) {
+    // shape guard: the tensor maps and tile geometry come from a HOST copy of the level shapes; the operator's contract
+    // is the DEVICE tensors (ms_deform_attn_cuda.cu:20-80 reads them in-kernel).  If they disagree this kernel does
+    // nothing and tells the register-gather launch that follows to serve every query.
+    bool bad = false;
+    for (int l = 0; l < NL; ++l)
+      bad = bad || p.shapes[2 * l] != (int64_t)geo.H[l] || p.shapes[2 * l + 1] != (int64_t)geo.W[l] || p.lsi[l] != (int64_t)geo.start[l];
+    sMismatch = bad ? 1 : 0;
+    if (bad && p.shape_flag) {
+      *p.shape_flag = p.shape_epoch;
+      if (p.shape_report) *reinterpret_cast<volatile int*>(p.shape_report) = p.shape_epoch;
+    }
+  }
   if (tid == 0) {
     for (int l = 0; l < NL; ++l) {
       mbar_init(smem_u32(&sFull[l]), 1);
@@ -94,6 +108,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
     mbar_fence_init();
   }
   __syncthreads();
+  if (sMismatch) return;
 
   const uint32_t sWinBase = smem_u32(pl_smem + kPlRecBytes);
   const int cstride = M * kPlRowB;
@@ -355,11 +370,10 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
 template <bool FUSED>
 int launch_pipelined(const FwdParams& p, const PipeGeom& geo, cudaStream_t stream) {
   auto kern = msda_fwd_pipelined_kernel<FUSED>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;   // function attributes are per device
+  if (configured.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
   }
   kern<<<p.grid, pl_threads(FUSED), kPlSmem, stream>>>(p, geo);
   return (int)cudaGetLastError();

@@ -444,12 +444,11 @@ bool make_window_maps(const FwdParams& p, StagedMaps& maps) {
 template <bool FUSED, int DBG, bool TMA>
 int launch_staged_impl(const FwdParams& p, const StagedMaps& maps, cudaStream_t stream) {
   auto kern = msda_fwd_staged_kernel<FUSED, DBG, TMA>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;   // function attributes are per device
+  if (configured.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmem);
     if (e != cudaSuccess) return (int)e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // two ~98 KB CTAs per SM
-    configured = true;
   }
   kern<<<p.grid, kSgThreads, kSgSmem, stream>>>(p, maps);
   return (int)cudaGetLastError();

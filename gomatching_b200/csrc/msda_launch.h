@@ -5,6 +5,20 @@
 
 namespace msda {
 
+// "once per device" latch for cudaFuncSetAttribute calls: the attributes belong to the (function, device) pair, so a
+// process-wide flag would leave a second GPU of the same process without its shared-memory opt-in.  Benign race:
+// the guarded calls are idempotent.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 enum TileMode { kModeLinear = 1, kModePyramid = 2, kModeGeneric = 3, kModeStaged = 4, kModePipelined = 5 };
 
 struct FwdParams {
@@ -32,6 +46,12 @@ struct FwdParams {
   int walk;                   // fast kernels: 0 strided heads-fastest tile walk, 1 contiguous raster walk per CTA (diagnostic)
   int q_level_begin;          // fast kernels, linear mode: only queries >= level_start_index[q_level_begin] (self-attention)
   int staged_levels;          // staged mode: query levels 0 .. staged_levels-1 run the shared-memory-window kernel
+  // shape guard (pipelined mode): the window kernel compares the device-side shapes with the host-side geometry its
+  // tensor maps were built from; on a mismatch it writes shape_epoch to *shape_flag (and to *shape_report, pinned host
+  // memory) and does nothing, and the register-gather launch that follows serves ALL queries instead of levels 1..3
+  int* shape_flag;
+  int* shape_report;
+  int shape_epoch;
 };
 
 // Each returns a cudaError_t cast to int (0 = ok) or MSDA_E_UNSUPPORTED (-5).
@@ -56,6 +76,10 @@ bool staged_get_host_shapes(long long (*hw)[2], long long* lsi);   // 4 levels; 
 // producer / consumer version of the staged kernel (msda_forward_pipelined.cu): level-0 queries only, needs the hint;
 // MSDA_E_UNSUPPORTED if it cannot run (the caller falls back)
 int launch_forward_pipelined_f32(const FwdParams& p, const long long (*hw)[2], const long long* lsi, cudaStream_t stream);
+// shape guard: a flag slot + a fresh epoch for one pipelined launch pair; MSDA_E_UNSUPPORTED while the stream is being
+// captured and the guard's buffers do not exist yet (they are allocated on first use, outside capture)
+int shape_guard_acquire(int** flag, int** report, int* epoch, cudaStream_t stream);
+int shape_guard_last_mismatch();   // epoch of the most recent mismatch any kernel reported (0: none); a stale read is fine
 // true if the tiled kernels can run this problem (else only the generic kernel can)
 bool tiled_supported(int elem_bytes, int D, int L, int P, bool fused);
 

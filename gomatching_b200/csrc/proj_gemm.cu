@@ -26,6 +26,7 @@
 
 #include "../../include/msda_b200.h"
 #include "tma_common.cuh"
+#include "msda_launch.h"
 
 namespace msda {
 namespace {
@@ -376,11 +377,10 @@ static int linear_impl(const float* x, int ldx, const float* w_hi, const float* 
   const size_t stage_need = (size_t)4 * (two ? 8 : 4) * 4096;   // epilogue staging: 4 warps x G slabs x 4 KB
   if (smem < stage_need) smem = stage_need;
   smem += 1024;                                  // alignment slack
-  static bool configured = false;
-  if (!configured) {
+  static msda::PerDeviceOnce configured;   // function attributes are per device
+  if (configured.need()) {
     cudaFuncSetAttribute(proj_gemm_3xtf32_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     cudaFuncSetAttribute(proj_gemm_3xtf32_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
   }
   dim3 grid((M + block_m - 1) / block_m, n_tiles);
   if (two)

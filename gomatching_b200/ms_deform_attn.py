@@ -93,7 +93,7 @@ class MSDeformAttn(nn.Module):
         return self._qproj_cache[1], self._qproj_cache[2]
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None):
+                input_padding_mask=None, spatial_shapes_list=None):
         """
         :param query                       (N, Length_{query}, C)
         :param reference_points            (N, Length_{query}, n_levels, 2) in [0, 1], or (..., 4) reference boxes
@@ -101,6 +101,8 @@ class MSDeformAttn(nn.Module):
         :param input_spatial_shapes        (n_levels, 2) int64 [(H_0, W_0), ...]
         :param input_level_start_index     (n_levels,) int64
         :param input_padding_mask          (N, sum_l H_l*W_l) bool, True for padding
+        :param spatial_shapes_list         optional (not in the reference): the same shapes as Python ints, saves the
+                                           one device->host read per new pyramid of the TMA window kernel
         :return output                     (N, Length_{query}, C)
         """
         N, Len_q, _ = query.shape
@@ -119,7 +121,8 @@ class MSDeformAttn(nn.Module):
         C = self.d_model
         tc = (self.tensor_core_projections and not needs_grad and query.is_cuda and input_flatten.is_cuda
               and query.dtype == torch.float32 and input_flatten.dtype == torch.float32
-              and self.value_proj.weight.dtype == torch.float32 and C % 32 == 0 and (M * L * P) % 32 == 0)
+              and self.value_proj.weight.dtype == torch.float32 and C % 32 == 0 and (M * L * P) % 32 == 0
+              and C <= 1024 and 3 * M * L * P <= 1024)       # the GEMM kernel's limits (projections.linear_impl)
 
         if tc:
             value = linear_3xtf32(input_flatten, self.value_proj.weight, self.value_proj.bias,
@@ -152,7 +155,7 @@ class MSDeformAttn(nn.Module):
             output = ms_deform_attn_forward_fused(
                 value.contiguous(), input_spatial_shapes, input_level_start_index,
                 reference_points.float().contiguous(), sampling_offsets.float(), attention_weights.float(),
-                tuning=self.tuning)
+                tuning=self.tuning, spatial_shapes_list=spatial_shapes_list)
         else:
             attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
             if reference_points.shape[-1] == 2:

@@ -56,8 +56,12 @@ def _check_im2col_step(N: int, im2col_step: int) -> None:
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64,
-                           tuning=None):
-    """Same call as ``adet._C.ms_deform_attn_forward``; returns (N, Lq, M*D)."""
+                           tuning=None, spatial_shapes_list=None):
+    """Same call as ``adet._C.ms_deform_attn_forward``; returns (N, Lq, M*D).
+
+    ``spatial_shapes_list`` (optional, [(H_l, W_l), ...] Python ints -- the list the caller built the tensor from,
+    deformable_transformer.py:157-169) saves the one device->host read per new pyramid that the TMA window kernel's
+    tensor maps otherwise cost; results never depend on it (the kernels validate it against the device tensor)."""
     N, S, M, D, L, Lq, P = _check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     _check_im2col_step(N, im2col_step)
     lib = _native.lib()
@@ -80,9 +84,8 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     loc = sampling_loc if sampling_loc.dtype == torch.float32 else sampling_loc.float()
     attn = attn_weight if attn_weight.dtype == torch.float32 else attn_weight.float()
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-    if _native.tuning_mode(tuning) in (4, 5):
-        _native.staged_shape_hint(spatial_shapes, level_start_index)
     with torch.cuda.device(value.device):
+        tuning = _native.auto_window_tuning(value, spatial_shapes, level_start_index, Lq, tuning, spatial_shapes_list)
         stream = torch.cuda.current_stream().cuda_stream
         rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), loc.data_ptr(),
                 attn.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(), stream, _native.make_tuning(tuning))
@@ -107,7 +110,7 @@ def _row_pitch(t, row_len):
 
 
 def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
-                                 attention_logits, n_points=None, tuning=None):
+                                 attention_logits, n_points=None, tuning=None, spatial_shapes_list=None):
     """softmax(logits) + offsets->locations + sampling + weighted reduction in one kernel.
 
     value (N,S,M,D) fp32|bf16; reference_points (N,Lq,L,2|4) fp32; sampling_offsets (N,Lq,M,L,P,2) fp32 (raw
@@ -143,10 +146,13 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
         raise RuntimeError("msda_b200: value dtype %s has no kernel" % value.dtype)
     f32 = value.dtype == torch.float32
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-    if _native.tuning_mode(tuning) in (4, 5):
-        _native.staged_shape_hint(spatial_shapes, level_start_index)
     with torch.cuda.device(value.device):
+        tuning = _native.auto_window_tuning(value, spatial_shapes, level_start_index, Lq, tuning, spatial_shapes_list)
         stream = torch.cuda.current_stream().cuda_stream
+        log = _native.event_log
+        if log is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if pitched:
             fn = lib.msda_b200_forward_fused_pitched_f32 if f32 else lib.msda_b200_forward_fused_pitched_bf16
             rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
@@ -158,6 +164,10 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
             rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                     reference_points.data_ptr(), ref_dim, sampling_offsets.data_ptr(), attention_logits.data_ptr(), N, S,
                     M, D, L, Lq, P, out.data_ptr(), stream, _native.make_tuning(tuning))
+        if log is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            log.append((("fused", N, S, Lq, str(value.dtype)), ev0, ev1))
     _native.check(rc, "ms_deform_attn_forward_fused")
     return out
 

@@ -78,6 +78,9 @@ class _Association(threading.Thread):
             item = self.q.get()
             if item is None:
                 return
+            if isinstance(item, threading.Event):        # flush marker: everything queued before it is done
+                item.set()
+                continue
             records, frames, ready = item
             if ready is not None:
                 self.stream.wait_event(ready)
@@ -95,7 +98,8 @@ class ClipTracker:
 
     def __init__(self, model, schema: Optional[RecordSchema] = None, weights: Optional[Sequence[int]] = None,
                  tracker_rank: int = 0, overlap: bool = True, group=None, frame_size: Optional[Tuple[int, int]] = None,
-                 use_batcher: Optional[bool] = None, input_format: str = "RGB"):
+                 use_batcher: Optional[bool] = None, input_format: str = "RGB", associate: bool = True,
+                 host_results: bool = False):
         self.model = model
         self.group = group
         self.rank, self.world = _world(group)
@@ -120,6 +124,9 @@ class ClipTracker:
                                          "long_match", "short_match", "post_process")}
         self.spot_s = 0.0
         self.assoc_inline_s = 0.0
+        self.associate = associate            # False: records are gathered and dropped (spotting-only measurement)
+        self.host_results = host_results      # True: every frame's track ids are copied to the host as they are assigned
+        self.host_ids: list = []
         self._worker: Optional[_Association] = None
         if overlap and self.rank == tracker_rank:
             self._worker = _Association(self)
@@ -172,6 +179,8 @@ class ClipTracker:
 
     # ------------------------------------------------------------------------------------------ association
     def _associate_round(self, records: torch.Tensor, frames: List[int]):
+        if not self.associate:
+            return
         for row, t in zip(records, frames):
             fields, frame_index, size = self.schema.unpack(row)
             assert frame_index == t == len(self.instances), "gather lost the frame order"
@@ -180,6 +189,8 @@ class ClipTracker:
                 inst.set(k, self._Boxes(v) if k == "pred_boxes" else v)
             self.instances.append(inst)
             self.instances, self.id_count = reference_association_step(self.model, self.instances, t, self.id_count)
+            if self.host_results:
+                self.host_ids.append(self.instances[-1].track_ids.cpu())
 
     # ------------------------------------------------------------------------------------------ driver
     @torch.no_grad()
@@ -225,6 +236,18 @@ class ClipTracker:
             bucket = list(out.unbind(0))
         dist.gather(block, bucket, dst=self.tracker_rank, group=self.group)
         return out
+
+    def flush(self) -> None:
+        """Block until every frame fed so far has been associated; the worker stays alive (tracker rank; no-op
+        elsewhere).  bench.py brackets its timed region with this."""
+        if self._worker is not None:
+            marker = threading.Event()
+            self._worker.q.put(marker)
+            while not marker.wait(0.05):
+                if not self._worker.is_alive():
+                    break
+            if self._worker.error is not None:
+                raise self._worker.error
 
     def drain(self) -> None:
         """Block until every fed frame has been associated (tracker rank; no-op elsewhere).  Ends the worker."""

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 1
+#define MSDA_B200_ABI_VERSION 2
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define MSDA_E_NULLPTR   (-1)   /* a required pointer is NULL                                   */
@@ -193,6 +193,15 @@ int msda_b200_linear_relu_f32(const float* x, int ldx, const float* w_hi, const 
  * (device memory, [CTAs][8] int64: start, first stage full, split done, last MMA issued, accumulator ready,
  * epilogue done); NULL switches tracing off.  tools/gemm_trace.py. */
 void msda_b200_linear_set_trace(long long* buf);
+
+/* ---- shape guard of the TMA window kernel (tuning mode 5, the default for fp32 encoder self-attention) ---------
+ * The window kernel builds its tensor maps from a HOST copy of the level shapes (msda_b200_staged_set_host_shapes);
+ * the operator's contract is the DEVICE tensors, which the reference reads in-kernel (ms_deform_attn_cuda.cu:20-80,
+ * ms_deform_im2col_cuda.cuh:272-278).  Every launch therefore checks the two against each other on the device; on a
+ * mismatch the window kernel does nothing, the register-gather launch that follows it serves every query (results are
+ * always those of the device tensors), and the epoch of the launch is stored in pinned host memory.  This returns the
+ * most recent such epoch (0: never) without synchronising -- the caller polls it to drop a stale host-side cache. */
+int msda_b200_shape_mismatch_epoch(void);
 
 /* ---- host-buffer entry: what a non-PyTorch host (the cgo/JNI/ctypes stub of INTEGRATION.md) calls --
  * All tensor pointers are HOST pointers (pinned for full PCIe speed, pageable works).  Copies the

@@ -1,0 +1,145 @@
+"""GPU acceptance tests of the video path with the REFERENCE's real model (north_star: "end-to-end MOTA/IDF1 on a
+synthetic clip must be identical").
+
+The clip: 24 seeded 1280x720 frames; the model: the reference's GoMatching (ResNet-50 + 6+6-layer DeepSolo +
+LSTMatcher) at its own default initialisation (with WITH_RESR the rescoring head passes 30-100 detections per frame).
+  reference arm   the reference's serial loop (GoMatching.batch_inference), its own modules, and the UNMODIFIED
+                  reference CUDA kernel (oracle/_ref/libmsda_refcuda.so) behind adet._C.ms_deform_attn_forward
+  B200 arm        ClipTracker (frame batcher kernel, sharded rounds, record gather, association thread) around the
+                  same model object API, with the B200 operator installed at level "op" (kernel swap only: must be
+                  IDENTICAL, bit for bit, down to every track ID) or "layers" (the whole drop-in stack: fused glue,
+                  tensor-core projections, fused add+LayerNorm -- fp32-rounding-level differences in the features,
+                  checked within tolerance; identity flips at near-ties are counted and bounded)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import clip_common as C
+from gomatching_b200.video.tracking import ClipTracker
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not C.have_reference(), reason="reference Python not staged (baseline/_ref)")]
+
+H, W, N_FRAMES = 720, 1280, 24
+
+
+@pytest.fixture(scope="module")
+def reference_run():
+    if not os.path.exists(C.REFCUDA):
+        pytest.skip("oracle/_ref/libmsda_refcuda.so not built")
+    cfg = C.L.build_cfg(device="cuda")
+    frames = C.L.synthetic_clip(N_FRAMES, H, W, seed=1)
+    model = C.L.build_gomatching(cfg, seed=0)
+    assert C.use_reference_cuda_kernel()
+    ref, id_count = C.reference_loop(model, frames)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    C.L.restore_reference_classes()
+    return cfg, frames, sd, C.summarize(ref), id_count
+
+
+def test_operator_swap_leaves_every_track_id_identical(reference_run):
+    cfg, frames, sd, ref, id_count = reference_run
+    n = [len(r[0]) for r in ref]
+    assert min(n) >= 10 and id_count > max(n), (n, id_count)           # a non-trivial clip
+    model = C.L.build_gomatching(cfg, seed=0, b200="op", state_dict=sd)
+    for overlap in (False, True):
+        ct = ClipTracker(model, overlap=overlap)                        # uint8 frames -> frame batcher kernel
+        ct.feed(frames[:10])
+        ct.feed(frames[10:])
+        got = C.summarize(ct.finish())
+        C.assert_identical(ref, got, "B200 operator, overlap=%s" % overlap)
+        assert ct.id_count == id_count
+        assert C.same_scores(C.mot_scores(ref, ref), C.mot_scores(got, ref))        # identical MOTA / IDF1
+
+
+def _spotter_outputs(model, frame):
+    with torch.no_grad():
+        images = model.preprocess_image([frame])
+        features, pos = model.backbone(images)
+        out = model.detection_transformer(features, pos, model.backbone)
+        out["re_pred_logits"] = model.roi_heads.rescoring_head(out["query_features"])
+    return {k: v.double() for k, v in out.items() if v is not None}
+
+
+@pytest.mark.parametrize("level", ["module", "layers"])
+def test_dropin_module_and_layers_stay_within_tolerance(reference_run, level):
+    """Levels "module" / "layers" (fused glue, tensor-core projections, fused add+LayerNorm)
+    change the summation order of the dense projections, so the spotter's outputs move at fp32 rounding level
+    (bar: 1e-4 of max|ref|, the operator's fp32 bar).  Discrete decisions downstream (NMS order, Hungarian) can then
+    flip at near-ties -- which a default-initialised model has in abundance (near-duplicate boxes) -- so identity of
+    track IDs is asserted for level "op" only; here the raw outputs are checked, and the clip-level effect is
+    bounded and printed."""
+    cfg, frames, sd, ref, id_count = reference_run
+    ref_model = C.L.build_gomatching(cfg, seed=0, state_dict=sd)
+    assert C.use_reference_cuda_kernel()
+    inputs = C.L.frames_to_inputs(frames[:2])
+    want = [_spotter_outputs(ref_model, f) for f in inputs]
+    del ref_model
+    model = C.L.build_gomatching(cfg, seed=0, b200=level, state_dict=sd)
+    for f, w in zip(inputs, want):
+        got = _spotter_outputs(model, f)
+        for k in w:
+            err = float((w[k] - got[k]).abs().max() / w[k].abs().max())
+            assert err <= 1e-4, "%s: %s moved by %.3g of max|ref|" % (level, k, err)
+    ct = ClipTracker(model, overlap=True)
+    ct.feed(frames)
+    got = C.summarize(ct.finish())
+    assert len(got) == len(ref)
+    n_ref, n_got = [len(a[0]) for a in ref], [len(b[0]) for b in got]
+    same = sum(int(np.array_equal(a[0], b[0])) for a, b in zip(ref, got))
+    sa, sb = C.mot_scores(ref, ref), C.mot_scores(got, ref)
+    print("level %s: %d of %d frames with identical track ids; detections per frame %s vs %s; MOTA %.4f vs %.4f, "
+          "IDF1 %.4f vs %.4f" % (level, same, len(ref), n_ref[:8], n_got[:8], sa["mota"], sb["mota"], sa["idf1"], sb["idf1"]))
+    assert max(abs(a - b) for a, b in zip(n_ref, n_got)) <= 5
+    assert np.isfinite(sb["mota"]) and np.isfinite(sb["idf1"])
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg = C.L.build_cfg(device="cuda:%d" % rank)
+        model = C.L.build_gomatching(cfg, seed=0, b200="layers")
+        frames = C.L.synthetic_clip(N_FRAMES, H, W, seed=1)
+        ct = ClipTracker(model, overlap=True, weights=[1] + [2] * (world - 1))
+        ct.feed(frames)
+        res = ct.finish()
+        if rank == 0:
+            q.put((C.summarize(res), ct.id_count))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_sharded_clip_identical_to_one_gpu():
+    """W GPUs (NCCL record gather) vs one GPU, full drop-in stack on both sides: identical track IDs."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    cfg = C.L.build_cfg(device="cuda:0")
+    model = C.L.build_gomatching(cfg, seed=0, b200="layers")
+    frames = C.L.synthetic_clip(N_FRAMES, H, W, seed=1)
+    ct = ClipTracker(model, overlap=False)
+    ct.feed(frames)
+    one = C.summarize(ct.finish())
+    one_count = ct.id_count
+    del model, ct
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = C.free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, got_count = q.get()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    C.assert_identical(one, got, "NCCL world %d" % world)
+    assert got_count == one_count

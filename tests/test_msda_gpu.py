@@ -581,3 +581,101 @@ def test_module_tensor_core_projections_match_cublas_fp32(module_cases):
             mod.tensor_core_projections = False
             b = mod(*args)
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# The TMA window kernel as the DEFAULT encoder path: host geometry keyed by value, validated on the device
+# ---------------------------------------------------------------------------------------------------
+def _encoder_workload(h, w, seed, transpose=False):
+    """fp32 encoder self-attention workload on an (h, w) frame; ``transpose`` swaps H and W of every level, which keeps
+    S (and every other host-visible size) but is a different pyramid."""
+    from gomatching_b200 import synthetic as syn
+    wk = syn.make_workload("encoder", h, w, n=2, seed=seed, dist="uniform")
+    shapes = wk.shapes.clone()
+    if transpose:
+        shapes = shapes.flip(1).contiguous()
+    return dict(value=wk.value.numpy(), shapes=shapes.numpy(), lsi=wk.lsi.numpy(), loc=wk.loc.numpy(), attn=wk.attn.numpy())
+
+
+def test_window_kernel_is_the_default_and_its_shape_guard_holds():
+    """(1) Without any tuning the fp32 encoder call learns the pyramid once and runs mode 5; bits == mode 1 == oracle.
+    (2) A second pyramid with the SAME S (H and W swapped) hits the value-keyed cache with the wrong geometry: the
+    device-side guard must make the result that of the device tensors anyway, report the mismatch, and the cache must
+    relearn.  (3) A wrong ``spatial_shapes_list`` is equally harmless."""
+    from gomatching_b200 import _native
+    import gomatching_b200 as g
+    _native._window_geometry.clear()
+    a = _encoder_workload(96, 160, 21)
+    b = _encoder_workload(96, 160, 22, transpose=True)
+    learned0 = _native.window_stats["learned"]
+    out_a = run_core(a).cpu().numpy()                                  # auto -> mode 5
+    assert _native.window_stats["learned"] == learned0 + 1
+    assert np.array_equal(out_a, run_core(a, dict(mode=1)).cpu().numpy())
+    assert np.array_equal(out_a, O.forward_f32(a["value"], a["shapes"], a["lsi"], a["loc"], a["attn"]))
+    run_core(a)
+    assert _native.window_stats["learned"] == learned0 + 1             # no second device->host read
+    ep0 = _native.lib().msda_b200_shape_mismatch_epoch()
+    out_b = run_core(b).cpu().numpy()                                  # cache says pyramid A: guard must catch it
+    want_b = O.forward_f32(b["value"], b["shapes"], b["lsi"], b["loc"], b["attn"])
+    assert np.array_equal(out_b, want_b), "stale host geometry changed the result"
+    torch.cuda.synchronize()
+    assert _native.lib().msda_b200_shape_mismatch_epoch() != ep0       # reported through pinned host memory
+    out_b2 = run_core(b).cpu().numpy()                                 # cache dropped and relearned for B
+    assert np.array_equal(out_b2, want_b) and _native.window_stats["learned"] == learned0 + 2
+    ep1 = _native.lib().msda_b200_shape_mismatch_epoch()
+    run_core(b)
+    torch.cuda.synchronize()
+    assert _native.lib().msda_b200_shape_mismatch_epoch() == ep1       # and no further mismatch
+    # (3) lying list: same S, wrong geometry
+    lie = [tuple(int(v) for v in hw) for hw in a["shapes"]]
+    out = g.ms_deform_attn_forward(dev(b["value"]), dev(b["shapes"]), dev(b["lsi"]), dev(b["loc"]), dev(b["attn"]), 64,
+                                   spatial_shapes_list=lie).cpu().numpy()
+    assert np.array_equal(out, want_b)
+    with pytest.raises(ValueError):
+        g.ms_deform_attn_forward(dev(b["value"]), dev(b["shapes"]), dev(b["lsi"]), dev(b["loc"]), dev(b["attn"]), 64,
+                                 spatial_shapes_list=[(1, 1)] * 4)
+    _native._window_geometry.clear()
+
+
+def test_window_kernel_default_under_cuda_graph_capture():
+    """Inside a capture an unknown pyramid cannot be learned (no device->host read): the call must fall back to the
+    register-gather kernel and still be capturable; a known pyramid captures the window kernel."""
+    from gomatching_b200 import _native
+    import gomatching_b200 as g
+    a = _encoder_workload(64, 96, 31)
+    t = {k: dev(v) for k, v in a.items()}
+    want = O.forward_f32(a["value"], a["shapes"], a["lsi"], a["loc"], a["attn"])
+    for known in (False, True):
+        _native._window_geometry.clear()
+        if known:
+            run_core(a)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            g.ms_deform_attn_forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["attn"], 64)    # warm-up outside capture
+            torch.cuda.synchronize()
+            if not known:
+                _native._window_geometry.clear()
+            with torch.cuda.graph(graph, stream=s):
+                out = g.ms_deform_attn_forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["attn"], 64)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want), known
+
+
+def test_1080p_encoder_bit_exact_vs_oracle_and_reference_kernel():
+    """BASELINE.json config 5 size (1080x1920, S = 43110): the default path (window kernel) against the CPU oracle and
+    the unmodified reference CUDA kernel -- not only against itself."""
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("encoder", 1080, 1920, n=1, seed=5, dist="local")
+    c = dict(value=w.value.numpy(), shapes=w.shapes.numpy(), lsi=w.lsi.numpy(), loc=w.loc.numpy(), attn=w.attn.numpy())
+    out = run_core(c)
+    ora = O.forward_f32(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"])
+    assert np.array_equal(out.cpu().numpy(), ora)
+    ref = _refcuda()
+    if ref is not None:
+        assert torch.equal(out, _run_refcuda(ref, w)), "differs from the reference CUDA kernel"
+    wd = syn.make_workload("decoder", 1080, 1920, n=1, seed=6, dist="local")
+    cd = dict(value=wd.value.numpy(), shapes=wd.shapes.numpy(), lsi=wd.lsi.numpy(), loc=wd.loc.numpy(), attn=wd.attn.numpy())
+    assert np.array_equal(run_core(cd).cpu().numpy(), O.forward_f32(cd["value"], cd["shapes"], cd["lsi"], cd["loc"], cd["attn"]))

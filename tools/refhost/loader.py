@@ -190,16 +190,15 @@ def build_cfg(config: str = "GoMatching_ICDAR15", device: str = "cpu", **overrid
 
 
 # ----------------------------------------------------------------------------------------------- model
-def build_gomatching(cfg, seed: int = 0, b200: bool = False, state_dict=None):
-    """Instantiate the reference's GoMatching with its own initialisers (seeded).  ``b200=True`` installs the
-    B200 operator / layers first (gomatching_b200.install_into_adet) so DeepSolo's encoder and decoder are built
-    from them; pass ``state_dict`` of a reference-built model to get identical weights."""
-    ns = load_reference()
+def build_gomatching(cfg, seed: int = 0, b200=False, state_dict=None):
+    """Instantiate the reference's GoMatching with its own initialisers (seeded).  ``b200`` (True = "layers", or
+    "op" / "module") installs the B200 operator / module / layers first (gomatching_b200.install_into_adet) so
+    DeepSolo's encoder and decoder are built from them; pass ``state_dict`` of a reference-built model to get identical weights."""
+    load_reference()
+    restore_reference_classes()
     if b200:
         import gomatching_b200
-        gomatching_b200.install_into_adet()
-    else:
-        restore_reference_classes()
+        gomatching_b200.install_into_adet(level="layers" if b200 is True else b200)
     torch.manual_seed(seed)
     model = D2.build_model(cfg)
     if state_dict is not None:
