@@ -56,7 +56,12 @@ def parse():
     ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (clip: 4, op: 8)")
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--level", default="layers", choices=["op", "module", "layers"], help="install_into_adet level (clip)")
+    ap.add_argument("--level", default="transformer", choices=["op", "module", "layers", "transformer"],
+                    help="install_into_adet level (clip)")
+    ap.add_argument("--no-graph", action="store_true", help="clip: eager spotter instead of the CUDA-graph replay")
+    ap.add_argument("--detections", type=int, default=40,
+                    help="clip: calibrate the score threshold on the first frame so that this many of the 100 queries pass "
+                         "(0: keep the config's 0.3, at which a default-initialised model passes all 100)")
     ap.add_argument("--tracker-frames", type=int, default=-1,
                     help="frames per step the tracker rank spots itself (clip, N > 1); -1 = same as the others")
     ap.add_argument("--dist", default="local", choices=["local", "uniform", "oor", "center"])
@@ -137,6 +142,8 @@ def clip_config(args):
                     "100 point-query proposals x 25 points, d=256, 8 heads, 4 levels, 4 points + LSTMatcher tracker in the "
                     "loop), default-initialised seeded weights, 1 frame per forward" % (args.height, args.width, args.height),
         "frame": "%dx%d" % (args.width, args.height),
+        "detections": ("score threshold calibrated on the first frame so that %d of the 100 queries pass (SURVEY s8d: 20-60; "
+                       "default-initialised scores are flat)" % args.detections) if args.detections > 0 else "config threshold 0.3",
         "l2": "every frame's forward streams > L2 of activations (the encoder feed-forward intermediate alone is 78 MB "
               "per layer); the op-level lines rotate buffer sets larger than L2",
     }
@@ -199,6 +206,8 @@ class CpuClip:
         self.L = L
         self.model = L.build_gomatching(L.build_cfg(device="cpu"), seed=0)
         self.inputs = L.frames_to_inputs(L.synthetic_clip(4, args.height, args.width, seed=1))
+        if args.detections > 0:
+            L.calibrate_detections(self.model, self.inputs[0], args.detections)
         self.k = 0
 
     def step(self):
@@ -510,6 +519,10 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
     cfg = Lr.build_cfg(device=str(device))
     model = Lr.build_gomatching(cfg, seed=0, b200=args.level)
     pool_n = 8
+    threshold = None
+    if args.detections > 0:
+        threshold = Lr.calibrate_detections(model, Lr.frames_to_inputs(Lr.synthetic_clip(1, args.height, args.width, seed=1))[0],
+                                            args.detections)
     clip = Lr.synthetic_clip(pool_n, args.height, args.width, seed=11 + rank)
     host_pool = [torch.from_numpy(f).pin_memory() for f in clip]
     dev_pool = [f.to(device) for f in host_pool]
@@ -523,10 +536,11 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
             return float(t.item())
         return x
 
-    def run(pool, n_steps, associate=True, host_results=False):
+    def run(pool, n_steps, associate=True, host_results=False, graph=None):
         """n_steps rounds after `warmup` untimed ones; returns (ms per step by CUDA events incl. the association tail,
         tracker, kernel event log, C-ABI calls)."""
-        ct = ClipTracker(model, weights=weights, overlap=True, associate=associate, host_results=host_results)
+        ct = ClipTracker(model, weights=weights, overlap=True, associate=associate, host_results=host_results,
+                         graph=False if args.no_graph else graph)
         k = [0]
 
         def one_round():
@@ -542,7 +556,7 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
         barrier()
         log = []
         _native.event_log = log
-        calls0 = _native.calls
+        calls0 = _native.calls + (ct.spotter_graph.replayed_calls if ct.spotter_graph else 0)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0 = ct.association_seconds()
         t0.record()
@@ -553,15 +567,22 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
         barrier()
         _native.event_log = None
         ms = reduce_max(t0.elapsed_time(t1) / n_steps)
-        info = {"calls": _native.calls - calls0, "assoc_ms_per_frame": (ct.association_seconds() - a0) * 1e3 / (n_steps * per_step),
+        info = {"calls": _native.calls + (ct.spotter_graph.replayed_calls if ct.spotter_graph else 0) - calls0, "assoc_ms_per_frame": (ct.association_seconds() - a0) * 1e3 / (n_steps * per_step),
                 "spot_ms_per_frame": None, "d2h": sum(t.numel() * t.element_size() for t in ct.host_ids[-n_steps * per_step:]) / n_steps
                 if host_results and rank == 0 else 0}
         ct.drain()
+        info["detections_per_frame"] = (sum(len(x) for x in ct.instances[-n_steps * per_step:]) / (n_steps * per_step)
+                                        if rank == 0 and associate and ct.instances else None)
+        info["graph"] = None if ct.spotter_graph is None else {"replays": ct.spotter_graph.replays, "failed": ct.spotter_graph.failed}
+        ct.close()
         return ms, info, log
 
     ms, info, log = run(dev_pool, steps)
     res = {"value": per_step / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": per_step, "weights": weights,
-           "launches": info["calls"] * world, "assoc_ms_per_frame": info["assoc_ms_per_frame"], "level": args.level}
+           "launches": info["calls"] * world, "assoc_ms_per_frame": info["assoc_ms_per_frame"], "level": args.level,
+           "detections_per_frame": info["detections_per_frame"], "graph": info["graph"], "score_threshold": threshold}
+    if not log:         # graph replay: the sampler launches are inside the graph; time them in a short eager pass of the same forward
+        _, _, log = run(dev_pool, 3, associate=False, graph=False)
     enc_us = [a.elapsed_time(b) * 1e3 for tag, a, b in log if tag[3] == tag[2]]       # Lq == S: encoder self-attention
     dec_us = [a.elapsed_time(b) * 1e3 for tag, a, b in log if tag[3] != tag[2]]
     if enc_us:
@@ -707,7 +728,8 @@ def main():
             "frames_per_step": clip["frames_per_step"], "round_weights": clip["weights"], "install_level": clip["level"],
             "parallelism": "frames sharded across GPUs (dp%d), N=1 per forward; one NCCL gather of the round's records to "
                            "rank 0; the reference's tracker on rank 0 in a worker thread" % world,
-            "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "spotting_only": clip["spotting_only"],
+            "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "detections_per_frame": clip["detections_per_frame"],
+            "score_threshold": clip["score_threshold"], "cuda_graph": clip["graph"], "spotting_only": clip["spotting_only"],
             "clocks": clocks, "e2e": clip.get("e2e"), "gpu_launches": clip["launches"],
             "gpu_launches_note": "kernel-launching C-ABI calls of libmsda_b200.so in the timed region, all ranks (each "
                                  "enqueues >= 1 kernel); cuDNN / cuBLAS kernels of the reference's eager code not counted",

@@ -36,13 +36,17 @@ def install_into_adet(level: str = "layers"):
                 within 1e-4 of the reference module).
       "layers"  ``adet.layers.deformable_transformer.DeformableTransformerEncoderLayer`` (:218) and
                 ``DeformableCompositeTransformerDecoderLayer`` (:326) -> the drop-in layers (default).
+      "transformer"  additionally ``DeformableTransformer`` / ``DeformableTransformerEncoder`` (:22, :280) -> subclasses
+                of the reference's own classes whose forwards never touch the host (transformer_dropin.py): same
+                arithmetic, bit-identical results, CUDA-graph capturable, and the level geometry reaches the TMA window
+                kernel as Python ints.
     Call after ``adet`` is importable and BEFORE the model is constructed; modules that are not imported yet are
     skipped."""
     import sys
     import types
 
-    if level not in ("op", "module", "layers"):
-        raise ValueError("level must be 'op', 'module' or 'layers', got %r" % (level,))
+    if level not in ("op", "module", "layers", "transformer"):
+        raise ValueError("level must be 'op', 'module', 'layers' or 'transformer', got %r" % (level,))
     c = sys.modules.get("adet._C")
     if c is None:
         c = types.ModuleType("adet._C")
@@ -57,10 +61,28 @@ def install_into_adet(level: str = "layers"):
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "MSDeformAttn"):
             mod.MSDeformAttn = MSDeformAttn
-        if level != "layers":
+        if level not in ("layers", "transformer"):
             continue
         if mod is not None and hasattr(mod, "DeformableTransformerEncoderLayer"):
             mod.DeformableTransformerEncoderLayer = DeformableTransformerEncoderLayer
         if mod is not None and hasattr(mod, "DeformableCompositeTransformerDecoderLayer"):
             mod.DeformableCompositeTransformerDecoderLayer = DeformableCompositeTransformerDecoderLayer
+    if level == "transformer":
+        from .transformer_dropin import make_dropin_classes
+        dt = sys.modules.get("adet.layers.deformable_transformer")
+        if dt is not None:
+            base = getattr(dt, "_msda_b200_reference_classes", None)
+            if base is None:                              # remember the reference's own classes: installs are repeatable
+                base = dt._msda_b200_reference_classes = (dt.DeformableTransformer, dt.DeformableTransformerEncoder)
+            saved = dt.DeformableTransformer, dt.DeformableTransformerEncoder
+            dt.DeformableTransformer, dt.DeformableTransformerEncoder = base
+            try:
+                new_t, new_e = make_dropin_classes(dt)
+            finally:
+                dt.DeformableTransformer, dt.DeformableTransformerEncoder = saved
+            dt.DeformableTransformer, dt.DeformableTransformerEncoder = new_t, new_e
+            for name in ("adet.modeling.model.detection_transformer_wobackbone", "adet.modeling.model.detection_transformer"):
+                mod = sys.modules.get(name)
+                if mod is not None and hasattr(mod, "DeformableTransformer"):
+                    mod.DeformableTransformer = new_t
     return c

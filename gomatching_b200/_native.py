@@ -243,8 +243,25 @@ def auto_window_tuning(value, spatial_shapes, level_start_index, Lq: int, tuning
         return tuning
     if (value.dtype == torch.float32 and Lq == S and D == 32 and L == 4 and os.environ.get("MSDA_B200_NO_WINDOW") != "1"
             and window_geometry(spatial_shapes, level_start_index, S, L, shapes_list)):
-        return _MODE5
+        # the window kernel gives each CTA (one per SM) a contiguous run of (frame, head, 8x16 tile) items and needs a
+        # couple of dozen of them to amortise its pipeline ramp: 720p, fused: 89.9 vs 77.3 us at 1 frame per launch,
+        # 150 vs 143 at 2, 522 vs 544 at 8 (profiles/r02_sweep_encoder_f1_f2.log)
+        h0, w0 = _window_geometry[(spatial_shapes.device.index, int(S), L)][2][:2]
+        items = N * M * ((h0 + 7) // 8) * ((w0 + 15) // 16)
+        if items >= WINDOW_MIN_ITEMS_PER_SM * _sm_count(value.device):
+            return _MODE5
     return None
+
+
+WINDOW_MIN_ITEMS_PER_SM = 24
+_sm_counts = {}
+
+
+def _sm_count(device) -> int:
+    n = _sm_counts.get(device.index)
+    if n is None:
+        n = _sm_counts[device.index] = int(lib().msda_b200_sm_count())
+    return n
 
 
 def tuning_mode(tuning) -> int:

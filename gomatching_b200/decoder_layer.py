@@ -74,7 +74,10 @@ class DeformableCompositeTransformerDecoderLayer(nn.Module):
             tgt2 = self.linear2(self.dropout3(self.activation(self.linear1(tgt))))
         return self._add_norm(tgt, tgt2, self.dropout4, self.norm3)
 
-    def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask=None):
+    accepts_spatial_shapes_list = True      # transformer_dropin passes the Python shape list down to MSDeformAttn
+
+    def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask=None,
+                spatial_shapes_list=None):
         # tgt, query_pos: (bs, n_q, n_pts, d_model)
         bs, n_q, n_pts, dim = tgt.shape
         # ---- intra: sequences of n_pts points, one per (batch, proposal); nn.MultiheadAttention wants (L, B, E)
@@ -95,7 +98,8 @@ class DeformableCompositeTransformerDecoderLayer(nn.Module):
             assert reference_points.shape[2] == n_pts
             ref = reference_points
         cross = self.attn_cross(self.with_pos_embed(tgt_inter, query_pos).flatten(1, 2), ref.flatten(1, 2), src,
-                                src_spatial_shapes, level_start_index, src_padding_mask).reshape(bs, n_q, n_pts, dim)
+                                src_spatial_shapes, level_start_index, src_padding_mask,
+                                spatial_shapes_list=spatial_shapes_list).reshape(bs, n_q, n_pts, dim)
         tgt = self._add_norm(tgt_inter.contiguous(), cross, self.dropout_cross, self.norm_cross)
         # ---- ffn
         return self.forward_ffn(tgt)

@@ -82,10 +82,13 @@ class DeformableTransformerEncoderLayer(nn.Module):
             return add_layernorm(src, src2, norm)
         return norm(src + dropout(src2))
 
-    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+    accepts_spatial_shapes_list = True      # transformer_dropin passes the Python shape list down to MSDeformAttn
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
+                spatial_shapes_list=None):
         # self attention
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
-                              padding_mask)
+                              padding_mask, spatial_shapes_list=spatial_shapes_list)
         src = self._add_norm(src, src2, self.dropout1, self.norm1)
         # ffn
         src = self.forward_ffn(src)

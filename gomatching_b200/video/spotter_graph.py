@@ -1,0 +1,159 @@
+"""CUDA-graph replay of the frame-local, static-shape part of ``GoMatching.inference``.
+
+At one frame per forward (the reference's video loop, gom_lstmatcher.py:369-372, and the only batch size that keeps its
+numerics) the spotter is launch-bound: about 1500 kernels per 1280x720 frame (ResNet-50, 6 + 6 transformer layers, the
+heads), 29 ms of Python and launch overhead around 8 ms of GPU work (profiles/r02_clip_probe.txt).  Everything from the
+uint8 frame to the detection heads' raw outputs has static shapes for a given frame size and -- with the host-free
+``DeformableTransformer`` of ``transformer_dropin`` -- never touches the host, so it is captured ONCE per frame size
+and replayed:
+
+    frame (uint8 HWC, static buffer) -> frame-batcher kernel -> backbone + positional encodings -> input_proj ->
+    encoder x6 -> proposals / top-k -> decoder x6 -> class / text / point / boundary heads -> rescoring head
+
+The data-dependent tail of ``inference`` (score threshold, NMS, the association head's FC on the kept queries,
+``Instances``) stays eager and stays the reference's code: the model object is not re-implemented, its sub-modules'
+``forward`` attributes are pointed at the replayed buffers for the duration of a call, so ``GoMatching.inference``
+itself (:268-351) still drives the frame.  The captured kernels are the ones eager execution launches, in the same
+order, so the outputs are bit-identical to the eager path (tests/test_clip_gpu.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .batcher import batch_frames
+
+__all__ = ["GraphedSpotter"]
+
+
+class _FrameGraph:
+    def __init__(self, owner: "GraphedSpotter", hw: Tuple[int, int]):
+        model = owner.model
+        h, w = hw
+        dev = owner.device
+        self.frame = torch.zeros((h, w, 3), dtype=torch.uint8, device=dev)
+
+        def body():
+            img = batch_frames(self.frame, owner.mean, owner.std, flip_channels=owner.flip)
+            images = owner.ImageList(img, [(h, w)])
+            features, pos = model.backbone(images)
+            out = model.detection_transformer(features, pos, model.backbone)
+            re = model.roi_heads.rescoring_head(out["query_features"]) if model.with_rescore else None
+            return img, out, re
+
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):                       # lazy initialisation (cuDNN plans, weight splits, shape caches) happens here
+                body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from .. import _native
+        calls0 = _native.calls
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.img, self.out, self.re = body()
+        self.calls = _native.calls - calls0          # kernel-launching C-ABI calls of this library inside one replay
+
+    def replay(self, frame: torch.Tensor):
+        self.frame.copy_(frame, non_blocking=True)
+        self.graph.replay()
+
+
+class GraphedSpotter:
+    """Attach to a reference-API GoMatching model on a CUDA device; ``enable()`` re-points the model's static-shape
+    sub-module forwards at graph replays, ``disable()`` restores eager execution."""
+
+    def __init__(self, model, image_list_cls, input_format: str = "RGB"):
+        self.model = model
+        self.ImageList = image_list_cls
+        self.device = torch.device(model.device)
+        cfg = model.cfg
+        self.mean, self.std = list(cfg.MODEL.PIXEL_MEAN), list(cfg.MODEL.PIXEL_STD)
+        self.flip = input_format == "RGB"
+        self.graphs: Dict[Tuple[int, int], _FrameGraph] = {}
+        self.current: Optional[_FrameGraph] = None
+        self.enabled = False
+        self.replays = 0
+        self.replayed_calls = 0                      # C-ABI kernel launches executed through graph replays so far
+        self.failed: Optional[str] = None
+        self._eager_preprocess = None
+
+    # -- the four call sites of GoMatching.inference (gom_lstmatcher.py:274-292) --------------------------------------
+    def _preprocess_image(self, batched_inputs):
+        frames = [x["image"] for x in batched_inputs]
+        if len(frames) != 1 or frames[0].dtype != torch.uint8 or frames[0].dim() != 3:
+            raise ValueError("the graphed spotter takes one uint8 (H, W, 3) frame per forward")
+        f = frames[0]
+        hw = (int(f.shape[0]), int(f.shape[1]))
+        g = self.graphs.get(hw)
+        if g is None:
+            if len(self.graphs) >= 4:                # a clip has one frame size; do not hoard activations of old ones
+                self.graphs.clear()
+            try:
+                with self.eager():
+                    g = _FrameGraph(self, hw)
+            except Exception as e:                   # not capturable in this configuration: stay eager, say why
+                self.failed = "%s: %s" % (type(e).__name__, e)
+                self.disable()
+                torch.cuda.synchronize(self.device)
+                return self.model.preprocess_image(batched_inputs)
+            self.graphs[hw] = g
+        g.replay(f)
+        self.replays += 1
+        self.replayed_calls += g.calls
+        self.current = g
+        return self.ImageList(g.img, [hw])
+
+    def _backbone(self, images):
+        return None, None                            # consumed only by detection_transformer, which is replayed too
+
+    def _detection_transformer(self, features, pos, backbone):
+        # fresh tensors: inference() and detection() modify their inputs in place (:590-603)
+        return {k: (v.clone() if v is not None else None) for k, v in self.current.out.items()}
+
+    def _rescoring_head(self, query_features):
+        return self.current.re.clone()
+
+    def enable(self):
+        if self.enabled:
+            return
+        m = self.model
+        self._eager_preprocess = m.__dict__.get("preprocess_image")
+        m.preprocess_image = self._preprocess_image
+        m.backbone.forward = self._backbone
+        m.detection_transformer.forward = self._detection_transformer
+        if m.with_rescore:
+            m.roi_heads.rescoring_head.forward = self._rescoring_head
+        self.enabled = True
+
+    def disable(self):
+        if not self.enabled:
+            return
+        m = self.model
+        if self._eager_preprocess is not None:
+            m.preprocess_image = self._eager_preprocess
+        else:
+            m.__dict__.pop("preprocess_image", None)
+        for mod in (m.backbone, m.detection_transformer, m.roi_heads.rescoring_head if m.with_rescore else None):
+            if mod is not None:
+                mod.__dict__.pop("forward", None)
+        self.enabled = False
+
+    class _Eager:
+        def __init__(self, sp):
+            self.sp = sp
+
+        def __enter__(self):
+            self.was = self.sp.enabled
+            self.sp.disable()
+
+        def __exit__(self, *a):
+            if self.was:
+                self.sp.enable()
+
+    def eager(self):
+        """Context manager: run the model's own forwards (used while a graph is being captured)."""
+        return GraphedSpotter._Eager(self)

@@ -99,7 +99,7 @@ class ClipTracker:
     def __init__(self, model, schema: Optional[RecordSchema] = None, weights: Optional[Sequence[int]] = None,
                  tracker_rank: int = 0, overlap: bool = True, group=None, frame_size: Optional[Tuple[int, int]] = None,
                  use_batcher: Optional[bool] = None, input_format: str = "RGB", associate: bool = True,
-                 host_results: bool = False):
+                 host_results: bool = False, graph: Optional[bool] = None):
         self.model = model
         self.group = group
         self.rank, self.world = _world(group)
@@ -133,6 +133,18 @@ class ClipTracker:
             self._worker.start()
         if self.use_batcher:
             self._install_batcher()
+        # CUDA-graph replay of the static-shape part of the spotter (video/spotter_graph.py): needs the host-free
+        # DeformableTransformer (install level "transformer") and the uint8 frame path
+        self.spotter_graph = None
+        tr = getattr(getattr(model, "detection_transformer", None), "transformer", None)
+        if graph is None:
+            graph = self.use_batcher and hasattr(tr, "_shape_tensors")
+        if graph:
+            if not self.use_batcher:
+                raise ValueError("graph=True needs the uint8 frame path (use_batcher) on a CUDA device")
+            from .spotter_graph import GraphedSpotter
+            self.spotter_graph = GraphedSpotter(model, self._ImageList, input_format)
+            self.spotter_graph.enable()
 
     # ------------------------------------------------------------------------------------------ spotting
     def _install_batcher(self):
@@ -248,6 +260,12 @@ class ClipTracker:
                     break
             if self._worker.error is not None:
                 raise self._worker.error
+
+    def close(self) -> None:
+        """Give the model back its own forwards (undo the graph / batcher patches)."""
+        if self.spotter_graph is not None:
+            self.spotter_graph.disable()
+        self.model.__dict__.pop("preprocess_image", None)
 
     def drain(self) -> None:
         """Block until every fed frame has been associated (tracker rank; no-op elsewhere).  Ends the worker."""

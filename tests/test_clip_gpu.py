@@ -143,3 +143,26 @@ def test_nccl_sharded_clip_identical_to_one_gpu():
         assert p.exitcode == 0
     C.assert_identical(one, got, "NCCL world %d" % world)
     assert got_count == one_count
+
+
+def test_host_free_transformer_and_graph_replay_are_bit_identical_to_eager_layers():
+    """Install level "transformer" only removes host round trips, and the CUDA-graph replay launches the kernels eager
+    execution launches: both must reproduce level "layers" bit for bit -- every detection, every track ID."""
+    cfg = C.L.build_cfg(device="cuda")
+    frames = C.L.synthetic_clip(12, H, W, seed=1)
+    runs = {}
+    sd = None
+    for name, level, graph in (("layers", "layers", False), ("transformer", "transformer", False), ("graph", "transformer", True)):
+        model = C.L.build_gomatching(cfg, seed=0, b200=level, state_dict=sd)
+        if sd is None:
+            sd = {k: v.clone() for k, v in model.state_dict().items()}
+        ct = ClipTracker(model, overlap=False, graph=graph)
+        ct.feed(frames)
+        runs[name] = (C.summarize(ct.finish()), ct.id_count)
+        if graph:
+            assert ct.spotter_graph.failed is None and ct.spotter_graph.replays == len(frames)
+        ct.close()
+        del model, ct
+    C.assert_identical(runs["layers"][0], runs["transformer"][0], "level transformer vs layers")
+    C.assert_identical(runs["layers"][0], runs["graph"][0], "graph replay vs eager")
+    assert runs["layers"][1] == runs["transformer"][1] == runs["graph"][1]

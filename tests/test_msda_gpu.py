@@ -597,7 +597,7 @@ def _encoder_workload(h, w, seed, transpose=False):
     return dict(value=wk.value.numpy(), shapes=shapes.numpy(), lsi=wk.lsi.numpy(), loc=wk.loc.numpy(), attn=wk.attn.numpy())
 
 
-def test_window_kernel_is_the_default_and_its_shape_guard_holds():
+def test_window_kernel_is_the_default_and_its_shape_guard_holds(monkeypatch):
     """(1) Without any tuning the fp32 encoder call learns the pyramid once and runs mode 5; bits == mode 1 == oracle.
     (2) A second pyramid with the SAME S (H and W swapped) hits the value-keyed cache with the wrong geometry: the
     device-side guard must make the result that of the device tensors anyway, report the mismatch, and the cache must
@@ -605,6 +605,7 @@ def test_window_kernel_is_the_default_and_its_shape_guard_holds():
     from gomatching_b200 import _native
     import gomatching_b200 as g
     _native._window_geometry.clear()
+    monkeypatch.setattr(_native, "WINDOW_MIN_ITEMS_PER_SM", 0)        # small test maps: take the window kernel anyway
     a = _encoder_workload(96, 160, 21)
     b = _encoder_workload(96, 160, 22, transpose=True)
     learned0 = _native.window_stats["learned"]
@@ -637,11 +638,12 @@ def test_window_kernel_is_the_default_and_its_shape_guard_holds():
     _native._window_geometry.clear()
 
 
-def test_window_kernel_default_under_cuda_graph_capture():
+def test_window_kernel_default_under_cuda_graph_capture(monkeypatch):
     """Inside a capture an unknown pyramid cannot be learned (no device->host read): the call must fall back to the
     register-gather kernel and still be capturable; a known pyramid captures the window kernel."""
     from gomatching_b200 import _native
     import gomatching_b200 as g
+    monkeypatch.setattr(_native, "WINDOW_MIN_ITEMS_PER_SM", 0)
     a = _encoder_workload(64, 96, 31)
     t = {k: dev(v) for k, v in a.items()}
     want = O.forward_f32(a["value"], a["shapes"], a["lsi"], a["loc"], a["attn"])

@@ -45,6 +45,8 @@ def main():
     ap.add_argument("--enc", type=int, default=6)
     ap.add_argument("--dec", type=int, default=6)
     ap.add_argument("--skip-ref", action="store_true")
+    ap.add_argument("--level", default="transformer")
+    ap.add_argument("--graph", type=int, default=1)
     a = ap.parse_args()
     torch.backends.cudnn.benchmark = False
     cfg = C.small_cfg(device="cuda", enc=a.enc, dec=a.dec)
@@ -63,24 +65,26 @@ def main():
         print("reference loop second pass: %.1f ms/frame" % ((time.perf_counter() - t0) / a.frames * 1e3))
         ref = C.summarize(ref)
     del ref_model
-    model = C.L.build_gomatching(cfg, seed=0, b200=True, state_dict=sd)
+    model = C.L.build_gomatching(cfg, seed=0, b200=a.level, state_dict=sd)
     for ov in (False, True):
         for rep in range(2):
-            ct = ClipTracker(model, overlap=ov)
+            ct = ClipTracker(model, overlap=ov, graph=bool(a.graph))
             torch.cuda.synchronize(); t0 = time.perf_counter()
             ct.feed(frames)
             res = ct.finish()
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
         got = C.summarize(res)
-        print("B200 ClipTracker overlap=%s: %.1f ms/frame (spot %.1f, association %.1f ms/frame)" % (
-            ov, dt / a.frames * 1e3, ct.spot_s / a.frames * 1e3, ct.association_seconds() / a.frames * 1e3))
+        print("B200 ClipTracker level=%s graph=%s overlap=%s: %.1f ms/frame (spot %.1f, association %.1f ms/frame) %s" % (
+            a.level, a.graph, ov, dt / a.frames * 1e3, ct.spot_s / a.frames * 1e3, ct.association_seconds() / a.frames * 1e3,
+            ("graph replays %d failed=%s" % (ct.spotter_graph.replays, ct.spotter_graph.failed)) if ct.spotter_graph else ""))
+        ct.close()
         if not a.skip_ref:
             same_ids = all(np.array_equal(x[0], y[0]) for x, y in zip(ref, got)) and len(ref) == len(got)
             md = max(float(np.abs(x[1] - y[1]).max()) if x[1].shape == y[1].shape and x[1].size else 0.0 for x, y in zip(ref, got))
             print("   track ids identical to the reference loop: %s; n/frame %s; max |box diff| %.3g px; id_count %d vs %d" % (
                 same_ids, [len(x[0]) for x in got][:6], md, ct.id_count, ref_count))
     acc, hs = stage_timer(model)
-    ct = ClipTracker(model, overlap=False)
+    ct = ClipTracker(model, overlap=False, graph=False)
     ct.feed(frames)
     ct.finish()
     for h in hs:

@@ -106,7 +106,9 @@ def load_reference(root: Optional[str] = None):
     ns = types.SimpleNamespace(root=root, msda=msda, dt=dt, roi=roi, meta=meta, C=stub,
                                original=dict(MSDeformAttn=msda.MSDeformAttn,
                                              EncoderLayer=dt.DeformableTransformerEncoderLayer,
-                                             DecoderLayer=dt.DeformableCompositeTransformerDecoderLayer))
+                                             DecoderLayer=dt.DeformableCompositeTransformerDecoderLayer,
+                                             Transformer=dt.DeformableTransformer,
+                                             Encoder=dt.DeformableTransformerEncoder))
     _loaded.update(root=root, ns=ns)
     return ns
 
@@ -134,6 +136,11 @@ def restore_reference_classes():
     ns.dt.MSDeformAttn = ns.original["MSDeformAttn"]
     ns.dt.DeformableTransformerEncoderLayer = ns.original["EncoderLayer"]
     ns.dt.DeformableCompositeTransformerDecoderLayer = ns.original["DecoderLayer"]
+    ns.dt.DeformableTransformer = ns.original["Transformer"]
+    ns.dt.DeformableTransformerEncoder = ns.original["Encoder"]
+    wob = sys.modules.get("adet.modeling.model.detection_transformer_wobackbone")
+    if wob is not None:
+        wob.DeformableTransformer = ns.original["Transformer"]
     use_reference_cpu_path()
 
 
@@ -207,6 +214,28 @@ def build_gomatching(cfg, seed: int = 0, b200=False, state_dict=None):
     for p in model.parameters():
         p.requires_grad_(False)
     return model
+
+
+@torch.no_grad()
+def calibrate_detections(model, frame_input, keep: int = 40) -> float:
+    """Pick the score threshold that lets about ``keep`` of the queries through on ``frame_input`` and install it the
+    way eval.py:219-220 does (INFERENCE_TH_TEST, and ASSO_THRESH_TEST tied to it).  A default-initialised model has
+    no sharp scores: at the config's 0.3 all 100 queries pass and the tracker sees 100 detections per frame, 5-10x a
+    real text video; SURVEY.md s8d asks for 20-60.  Returns the threshold."""
+    images = model.preprocess_image([frame_input])
+    features, pos = model.backbone(images)
+    out = model.detection_transformer(features, pos, model.backbone)
+    prob = out["pred_logits"].mean(-2).sigmoid()                       # gom_lstmatcher.py:592-601
+    scores = prob.max(-1)[0]
+    if model.with_rescore:
+        re = model.roi_heads.rescoring_head(out["query_features"]).mean(-2).sigmoid().max(-1)[0]
+        scores = torch.where(scores > re, scores, re)
+    s = scores.flatten().sort(descending=True)[0]
+    keep = max(1, min(int(keep), s.numel() - 1))
+    thr = float((s[keep - 1] + s[keep]) / 2)
+    model.test_score_threshold = thr
+    model.roi_heads.asso_thresh_test = thr
+    return thr
 
 
 def synthetic_clip(n_frames: int, height: int, width: int, seed: int = 0):
