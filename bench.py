@@ -465,6 +465,20 @@ def run_op_workload(args, world, rank, device, steps, warmup, barrier, with_e2e)
             w["value"] = w["value"].bfloat16()
         sub["encoder_bf16_F%d" % F] = line(time_launches(lambda w: launch(w), enc, 5), F, enc[0]["S"], enc[0]["Lq"], 2)
         sub["decoder_bf16_F%d" % F] = line(time_launches(lambda w: launch(w), dec, 5), F, dec[0]["S"], dec[0]["Lq"], 2)
+        # the bf16 operator MODE: neighbour-paired value layout (built outside the timed launch, like value itself)
+        for w in enc + dec:
+            w["paired"] = g.pair_value_bf16(w["value"], w["shapes"], w["lsi"])
+            w["value"] = None
+
+        def launch_paired(w):
+            return g.ms_deform_attn_forward_fused_paired(w["paired"], w["shapes"], w["lsi"], w["ref"], w["offsets"], w["logits"])
+        sub["encoder_bf16_paired_F%d" % F] = line(time_launches(launch_paired, enc, 5), F, enc[0]["S"], enc[0]["Lq"], 2)
+        sub["decoder_bf16_paired_F%d" % F] = line(time_launches(launch_paired, dec, 5), F, dec[0]["S"], dec[0]["Lq"], 2)
+        pv = torch.randn(F, enc[0]["S"], M, D, device=device)
+        t_pair = time_launches(lambda w: g.pair_value_bf16(pv, w["shapes"], w["lsi"]), enc[:1], 5)
+        sub["pair_value_bf16_F%d" % F] = {"us_per_launch": t_pair, "GBps": (pv.numel() * 4 + pv.numel() * 4) / t_pair / 1e3,
+                                          "note": "layout conversion fp32 (N,S,M,D) -> paired bf16 (N,M,S,2,D): read + write bytes"}
+        del pv
         del enc[:], dec[:]
         torch.cuda.empty_cache()
         big = [device_workload("encoder", 4, 400 + i, args.dist, device, 1080, 1920) for i in range(3)]

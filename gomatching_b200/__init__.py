@@ -6,12 +6,14 @@ Public surface (mirrors third_party/adet/layers/ms_deform_attn.py of the referen
     ms_deform_attn_forward       adet._C.ms_deform_attn_forward drop-in
     ms_deform_attn_backward      adet._C.ms_deform_attn_backward drop-in
     ms_deform_attn_forward_fused softmax + offsets->locations + sampler in one kernel
+    pair_value_bf16, ms_deform_attn_forward[_fused]_paired   the bf16 operator mode on the neighbour-paired value layout
     DeformableTransformerEncoderLayer  encoder layer drop-in (sampler + tensor-core feed-forward block)
     DeformableCompositeTransformerDecoderLayer  point-query decoder layer drop-in
     install_into_adet            monkey-patch the reference's import sites
 """
 from .ms_deform_attn_func import (MSDeformAttnFunction, _MSDeformAttnFunction, fused_supported, locations_softmax,
                                   ms_deform_attn_backward, ms_deform_attn_forward, ms_deform_attn_forward_fused,
+                                  ms_deform_attn_forward_fused_paired, ms_deform_attn_forward_paired, pair_value_bf16,
                                   sample_index)
 from .ms_deform_attn import MSDeformAttn
 from .encoder_layer import DeformableTransformerEncoderLayer
@@ -20,7 +22,8 @@ from .decoder_layer import DeformableCompositeTransformerDecoderLayer
 __all__ = [
     "MSDeformAttn", "MSDeformAttnFunction", "_MSDeformAttnFunction", "ms_deform_attn_forward",
     "ms_deform_attn_backward", "ms_deform_attn_forward_fused", "fused_supported", "sample_index",
-    "locations_softmax", "install_into_adet", "DeformableTransformerEncoderLayer",
+    "locations_softmax", "install_into_adet", "pair_value_bf16", "ms_deform_attn_forward_paired",
+    "ms_deform_attn_forward_fused_paired", "DeformableTransformerEncoderLayer",
     "DeformableCompositeTransformerDecoderLayer",
 ]
 

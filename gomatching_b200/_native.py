@@ -41,6 +41,9 @@ SYMBOLS = (
     "msda_b200_staged_set_host_shapes",
     "msda_b200_add_layernorm_f32",
     "msda_b200_shape_mismatch_epoch",
+    "msda_b200_pair_value_bf16",
+    "msda_b200_forward_paired_bf16",
+    "msda_b200_forward_fused_paired_bf16",
 )
 
 
@@ -128,6 +131,12 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_staged_set_host_shapes.argtypes = [vp, vp, ci]
         L.msda_b200_frames_u8_to_chw_f32.restype = ci
         L.msda_b200_frames_u8_to_chw_f32.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp]
+        L.msda_b200_pair_value_bf16.restype = ci
+        L.msda_b200_pair_value_bf16.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
+        L.msda_b200_forward_paired_bf16.restype = ci
+        L.msda_b200_forward_paired_bf16.argtypes = [vp] * 5 + [ci] * 7 + [vp, vp]
+        L.msda_b200_forward_fused_paired_bf16.restype = ci
+        L.msda_b200_forward_fused_paired_bf16.argtypes = [vp, vp, vp, vp, ci, vp, vp] + [ci] * 7 + [vp, vp]
         L.msda_b200_shape_mismatch_epoch.restype = ci
         L.msda_b200_shape_mismatch_epoch.argtypes = []
         if L.msda_b200_abi_version() != ABI_VERSION:

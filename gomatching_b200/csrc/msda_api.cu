@@ -203,6 +203,64 @@ const char* msda_b200_error_string(int code) {
   return "msda_b200: unknown error";
 }
 
+int msda_b200_pair_value_bf16(const void* value, int value_is_bf16, const int64_t* shapes, const int64_t* lsi, int N, int S,
+                              int M, int D, int L, void* paired, void* stream) {
+  if (!value || !shapes || !lsi || !paired) return MSDA_E_NULLPTR;
+  if (N <= 0 || S <= 0 || M <= 0 || L <= 0 || L > 16) return MSDA_E_DIMS;
+  if (D != 32) return MSDA_E_UNSUPPORTED;
+  if (!aligned16(value) || !aligned16(paired)) return MSDA_E_ALIGN;
+  if ((long long)S * 128 >= (1ll << 31)) return MSDA_E_DIMS;           // int32 byte offsets inside one head's map
+  const int sms = sm_count_current();
+  if (sms < 0) return sms;
+  return launch_pair_value(value, value_is_bf16, shapes, lsi, N, S, M, L, paired, sms, (cudaStream_t)stream);
+}
+
+static int forward_paired_common(const void* paired, const int64_t* shapes, const int64_t* lsi, const float* loc,
+                                 const float* attn, const float* ref, int ref_dim, const float* offsets, const float* logits,
+                                 int N, int S, int M, int D, int L, int Lq, int P, void* out, void* stream) {
+  const bool fused = loc == nullptr;
+  if (!paired || !shapes || !lsi || !out) return MSDA_E_NULLPTR;
+  if (fused ? (!ref || !offsets || !logits) : !attn) return MSDA_E_NULLPTR;
+  if (fused && ref_dim != 2 && ref_dim != 4) return MSDA_E_REFDIM;
+  int rc = check_dims(N, S, M, D, L, Lq, P, 4);
+  if (rc) return rc;
+  if (!(D == 32 && L == 4 && P == 4)) return MSDA_E_UNSUPPORTED;
+  if ((long long)S * 128 >= (1ll << 31)) return MSDA_E_DIMS;
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = paired; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.attn = attn;
+  p.ref = ref; p.offsets = offsets; p.logits = logits; p.ref_dim = ref_dim; p.out = out;
+  p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P;
+  p.off_pitch = M * L * P * 2; p.logit_pitch = M * L * P;
+  if (!aligned16(paired) || !aligned16(out)) return MSDA_E_ALIGN;
+  const uintptr_t a = fused ? (reinterpret_cast<uintptr_t>(offsets) | reinterpret_cast<uintptr_t>(logits) |
+                               reinterpret_cast<uintptr_t>(ref))
+                            : (reinterpret_cast<uintptr_t>(loc) | reinterpret_cast<uintptr_t>(attn));
+  if (a & 15u) return MSDA_E_ALIGN;
+  const int sms = sm_count_current();
+  if (sms < 0) return sms;
+  p.mode = kModeLinear;
+  p.tile_q = 64;
+  const long long tiles = (long long)N * M * ((Lq + p.tile_q - 1) / p.tile_q);
+  long long grid = (long long)sms * 4;
+  if (tiles < grid) grid = tiles;
+  p.grid = (int)(grid < 1 ? 1 : grid);
+  return launch_forward_paired_bf16(p, (cudaStream_t)stream);
+}
+
+int msda_b200_forward_paired_bf16(const void* paired, const int64_t* shapes, const int64_t* lsi, const float* loc,
+                                  const float* attn, int N, int S, int M, int D, int L, int Lq, int P, void* out, void* stream) {
+  if (!loc) return MSDA_E_NULLPTR;
+  return forward_paired_common(paired, shapes, lsi, loc, attn, nullptr, 2, nullptr, nullptr, N, S, M, D, L, Lq, P, out, stream);
+}
+
+int msda_b200_forward_fused_paired_bf16(const void* paired, const int64_t* shapes, const int64_t* lsi, const float* ref,
+                                        int ref_dim, const float* offsets, const float* logits, int N, int S, int M, int D,
+                                        int L, int Lq, int P, void* out, void* stream) {
+  return forward_paired_common(paired, shapes, lsi, nullptr, nullptr, ref, ref_dim, offsets, logits, N, S, M, D, L, Lq, P, out,
+                               stream);
+}
+
 int msda_b200_sm_count(void) { return sm_count_current(); }
 int msda_b200_variant_count(void) { return forward_variant_count(); }
 

@@ -76,6 +76,10 @@ bool staged_get_host_shapes(long long (*hw)[2], long long* lsi);   // 4 levels; 
 // producer / consumer version of the staged kernel (msda_forward_pipelined.cu): level-0 queries only, needs the hint;
 // MSDA_E_UNSUPPORTED if it cannot run (the caller falls back)
 int launch_forward_pipelined_f32(const FwdParams& p, const long long (*hw)[2], const long long* lsi, cudaStream_t stream);
+// neighbour-paired bf16 value layout (msda_forward_paired.cu): conversion and sampler (D = 32, L = 4, P = 4)
+int launch_pair_value(const void* value, int value_is_bf16, const int64_t* shapes, const int64_t* lsi, int N, int S, int M,
+                      int L, void* paired, int sms, cudaStream_t stream);
+int launch_forward_paired_bf16(const FwdParams& p, cudaStream_t stream);   // p.value = the paired tensor, p.out bf16
 // shape guard: a flag slot + a fresh epoch for one pipelined launch pair; MSDA_E_UNSUPPORTED while the stream is being
 // captured and the guard's buffers do not exist yet (they are allocated on first use, outside capture)
 int shape_guard_acquire(int** flag, int** report, int* epoch, cudaStream_t stream);

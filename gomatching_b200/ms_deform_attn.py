@@ -22,7 +22,8 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from .ms_deform_attn_func import (MSDeformAttnFunction, fused_supported, ms_deform_attn_forward_fused)
+from .ms_deform_attn_func import (ms_deform_attn_forward_fused_paired, pair_value_bf16,
+                                  MSDeformAttnFunction, fused_supported, ms_deform_attn_forward_fused)
 from .projections import linear_3xtf32
 
 
@@ -55,6 +56,9 @@ class MSDeformAttn(nn.Module):
         self.tensor_core_projections = True   # inference, fp32 CUDA: projections as 3xTF32 tcgen05 GEMMs (fp32-grade)
         self._qproj_cache = None
         self.tuning = None         # optional msda_b200_tuning_t fields (dict); never changes results
+        # opt-in bf16 operator mode (BASELINE.json config 3, bar 2e-2 vs the fp32 module): value is re-laid out as
+        # neighbour-paired bf16 (pair_value_bf16) and sampled by the paired kernel; D = 32, L = 4, P = 4, inference only
+        self.paired_bf16_value = False
 
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
@@ -151,7 +155,12 @@ class MSDeformAttn(nn.Module):
             sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
             attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
 
-        if fused_ok:
+        if fused_ok and self.paired_bf16_value and D == 32 and L == 4 and P == 4:
+            paired = pair_value_bf16(value.contiguous(), input_spatial_shapes, input_level_start_index)
+            output = ms_deform_attn_forward_fused_paired(
+                paired, input_spatial_shapes, input_level_start_index, reference_points.float().contiguous(),
+                sampling_offsets.float(), attention_weights.float()).to(query.dtype)
+        elif fused_ok:
             output = ms_deform_attn_forward_fused(
                 value.contiguous(), input_spatial_shapes, input_level_start_index,
                 reference_points.float().contiguous(), sampling_offsets.float(), attention_weights.float(),

@@ -172,6 +172,91 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
     return out
 
 
+def pair_value_bf16(value, spatial_shapes, level_start_index):
+    """value (N, S, M, D=32) float32 | bfloat16  ->  the neighbour-paired bf16 layout (N, M, S, 2, D) of the bf16 operator
+    mode (include/msda_b200.h): pair p = {pixel p, its right-hand neighbour in the same image row (zeros at the row end)}."""
+    _require(value.is_cuda, "Not implemented on the CPU")
+    _require(value.dim() == 4 and value.is_contiguous(), "value must be a contiguous (N, S, M, D) tensor")
+    _require(value.dtype in (torch.float32, torch.bfloat16), "pair_value_bf16 takes float32 or bfloat16 value")
+    _require(spatial_shapes.is_cuda and level_start_index.is_cuda and spatial_shapes.dtype == torch.int64
+             and level_start_index.dtype == torch.int64, "spatial_shapes / level_start_index must be CUDA int64 tensors")
+    N, S, M, D = value.shape
+    L = int(spatial_shapes.shape[0])
+    paired = torch.empty((N, M, S, 2, D), dtype=torch.bfloat16, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _native.lib().msda_b200_pair_value_bf16(value.data_ptr(), int(value.dtype == torch.bfloat16),
+                                                     spatial_shapes.contiguous().data_ptr(),
+                                                     level_start_index.contiguous().data_ptr(), N, S, M, D, L, paired.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "pair_value_bf16")
+    return paired
+
+
+def _check_paired(paired, spatial_shapes, level_start_index):
+    _require(paired.is_cuda, "Not implemented on the CPU")
+    _require(paired.dim() == 5 and paired.shape[3] == 2 and paired.dtype == torch.bfloat16 and paired.is_contiguous(),
+             "paired value must be a contiguous bfloat16 (N, M, S, 2, D) tensor (pair_value_bf16)")
+    _require(spatial_shapes.is_cuda and level_start_index.is_cuda and spatial_shapes.is_contiguous()
+             and level_start_index.is_contiguous() and spatial_shapes.dtype == torch.int64
+             and level_start_index.dtype == torch.int64, "spatial_shapes / level_start_index must be contiguous CUDA int64")
+    N, M, S, _, D = paired.shape
+    return N, S, M, D, int(spatial_shapes.shape[0])
+
+
+def ms_deform_attn_forward_paired(paired, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    """Core operator on the paired bf16 layout: same arguments as ``ms_deform_attn_forward`` with ``value`` replaced by
+    ``pair_value_bf16(value, ...)``.  Returns (N, Lq, M*D) bfloat16; 2e-2 bar vs the fp32 reference."""
+    N, S, M, D, L = _check_paired(paired, spatial_shapes, level_start_index)
+    _require(sampling_loc.is_cuda and attn_weight.is_cuda and sampling_loc.is_contiguous() and attn_weight.is_contiguous(),
+             "sampling_loc / attn_weight must be contiguous CUDA tensors")
+    _require(sampling_loc.dim() == 6 and tuple(sampling_loc.shape[:1] + sampling_loc.shape[2:4] + sampling_loc.shape[5:]) == (N, M, L, 2),
+             "sampling_loc shape does not match value")
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    _require(tuple(attn_weight.shape) == (N, Lq, M, L, P), "attn_weight shape does not match sampling_loc")
+    loc = sampling_loc if sampling_loc.dtype == torch.float32 else sampling_loc.float()
+    attn = attn_weight if attn_weight.dtype == torch.float32 else attn_weight.float()
+    out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=paired.device)
+    with torch.cuda.device(paired.device):
+        rc = _native.lib().msda_b200_forward_paired_bf16(paired.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                                         loc.data_ptr(), attn.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(),
+                                                         torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "ms_deform_attn_forward_paired")
+    return out
+
+
+def ms_deform_attn_forward_fused_paired(paired, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                        attention_logits):
+    """``ms_deform_attn_forward_fused`` on the paired bf16 layout."""
+    N, S, M, D, L = _check_paired(paired, spatial_shapes, level_start_index)
+    _require(sampling_offsets.dim() == 6 and sampling_offsets.shape[0] == N and sampling_offsets.shape[2] == M
+             and sampling_offsets.shape[3] == L and sampling_offsets.shape[5] == 2, "sampling_offsets shape does not match value")
+    Lq, P = sampling_offsets.shape[1], sampling_offsets.shape[4]
+    ref_dim = reference_points.shape[-1]
+    if ref_dim not in (2, 4):
+        raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(ref_dim))
+    _require(tuple(reference_points.shape) == (N, Lq, L, ref_dim), "bad reference_points shape")
+    _require(attention_logits.numel() == N * Lq * M * L * P, "bad attention_logits shape")
+    ref = reference_points.float().contiguous()
+    off = sampling_offsets.float().contiguous()
+    lg = attention_logits.float().contiguous()
+    _require(ref.is_cuda and off.is_cuda and lg.is_cuda, "reference_points / offsets / logits must be CUDA tensors")
+    out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=paired.device)
+    with torch.cuda.device(paired.device):
+        log = _native.event_log
+        if log is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        rc = _native.lib().msda_b200_forward_fused_paired_bf16(
+            paired.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), ref.data_ptr(), ref_dim, off.data_ptr(),
+            lg.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        if log is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            log.append((("fused_paired", N, S, Lq, "bf16_paired"), ev0, ev1))
+    _native.check(rc, "ms_deform_attn_forward_fused_paired")
+    return out
+
+
 def fused_supported(value_dtype, D: int, L: int, P: int) -> bool:
     """Shapes the fused kernel is instantiated for (csrc/msda_forward.cu tiled_supported)."""
     if value_dtype not in (torch.float32, torch.bfloat16) or L > 16:

@@ -194,6 +194,28 @@ int msda_b200_linear_relu_f32(const float* x, int ldx, const float* w_hi, const 
  * epilogue done); NULL switches tracing off.  tools/gemm_trace.py. */
 void msda_b200_linear_set_trace(long long* buf);
 
+/* ---- neighbour-paired bf16 value layout: an explicit operator MODE for the bf16 configuration ---------------------
+ * (BASELINE.json config 3; bar 2e-2 relative vs the fp32 reference.)  The reference has no half/bf16 path
+ * (AT_DISPATCH_FLOATING_TYPES, ms_deform_attn_cuda.cu:64); this mode stores value as
+ *     paired[b][m][p] = { value[b][p][m][0..D-1], value[b][p+1][m][0..D-1] }  bf16, 128 bytes, second half zero at the last
+ *                                                                            pixel of an image row
+ * i.e. (N, M, S, 2, D) instead of (N, S, M, D): both horizontal neighbours of a bilinear footprint share one 128-byte
+ * line (2 instead of 4 L1 wavefronts per sample) and a head's map is contiguous.  S, spatial_shapes and
+ * level_start_index keep their meaning.  D = 32 (pair_value); D = 32, L = 4, P = 4 (samplers).  Sampling indices are
+ * the same bits as every other kernel of this library; outputs are bf16 (N, Lq, M*D).
+ *   msda_b200_pair_value_bf16          builds the layout from value (N,S,M,D) fp32 (value_is_bf16 = 0) or bf16 (1)
+ *   msda_b200_forward_paired_bf16      core operator on it   (sampling_loc / attn_weight as in msda_b200_forward_f32)
+ *   msda_b200_forward_fused_paired_bf16  softmax + offsets->locations + sampler (as msda_b200_forward_fused_f32) */
+int msda_b200_pair_value_bf16(const void* value, int value_is_bf16, const int64_t* shapes, const int64_t* lsi,
+                              int N, int S, int M, int D, int L, void* paired, void* stream);
+int msda_b200_forward_paired_bf16(const void* paired, const int64_t* shapes, const int64_t* lsi,
+                                  const float* sampling_loc, const float* attn_weight,
+                                  int N, int S, int M, int D, int L, int Lq, int P, void* out, void* stream);
+int msda_b200_forward_fused_paired_bf16(const void* paired, const int64_t* shapes, const int64_t* lsi,
+                                        const float* reference_points, int ref_dim,
+                                        const float* sampling_offsets, const float* attention_logits,
+                                        int N, int S, int M, int D, int L, int Lq, int P, void* out, void* stream);
+
 /* ---- shape guard of the TMA window kernel (tuning mode 5, the default for fp32 encoder self-attention) ---------
  * The window kernel builds its tensor maps from a HOST copy of the level shapes (msda_b200_staged_set_host_shapes);
  * the operator's contract is the DEVICE tensors, which the reference reads in-kernel (ms_deform_attn_cuda.cu:20-80,
