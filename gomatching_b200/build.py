@@ -51,7 +51,7 @@ def have_nvcc() -> bool:
     return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, diag: bool = False) -> str:
     """No-op when the library is newer than every source.  Concurrent callers (one rank per GPU on a fresh checkout)
     are serialised by a file lock, and objects / the link output go to per-process temporaries before one atomic rename."""
     if not force and not _stale():
@@ -62,12 +62,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         try:
             if not force and not _stale():               # another process built it while this one waited
                 return LIB
-            return _build_locked(verbose)
+            return _build_locked(verbose, diag)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
-def _build_locked(verbose: bool) -> str:
+def _build_locked(verbose: bool, diag: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libmsda_b200.so cannot be built (there is no CPU fallback)")
@@ -75,7 +75,7 @@ def _build_locked(verbose: bool) -> str:
     procs = []
     for s in SOURCES:
         o = os.path.join(CSRC, s.replace(".cu", ".%d.o" % os.getpid()))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DMSDA_DIAG"] if diag else []), "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -94,7 +94,7 @@ def _build_locked(verbose: bool) -> str:
         raise RuntimeError("link failed:\n" + r.stdout)
     os.replace(tmp, LIB)
     with open(STAMP, "w") as f:
-        f.write(_source_hash() + "\n")
+        f.write((_source_hash() if not diag else "diagnostic build: always stale") + "\n")
     for o in objs:
         try:
             os.remove(o)
@@ -104,5 +104,5 @@ def _build_locked(verbose: bool) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv or "--diag" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv)
     print(path)

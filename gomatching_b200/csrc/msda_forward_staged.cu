@@ -491,12 +491,16 @@ bool staged_get_host_shapes(long long (*hw)[2], long long* lsi) {
 }
 
 int launch_forward_staged_f32(const FwdParams& p, cudaStream_t stream) {
-  if (p.loc != nullptr) {   // diagnostic variants (wrong results) exist for the core operator only
+#ifdef MSDA_DIAG
+  // Time-attribution builds that produce WRONG results (tools/sweep.py --staged-diag).  Compiled only with -DMSDA_DIAG
+  // (python -m gomatching_b200.build --diag): in the product library `variant` never changes results in any mode.
+  if (p.loc != nullptr) {
     if (p.variant == 1) return launch_staged<false, 1>(p, stream);    // no fallback path
     if (p.variant == 2) return launch_staged<false, 3>(p, stream);    // ... and no window fill
     if (p.variant == 3) return launch_staged<false, 5>(p, stream);    // ... no gather passes (fill only)
     if (p.variant == 4) return launch_staged<false, 7>(p, stream);    // ... neither: phase 1, records, barriers, stores
   }
+#endif
   return p.loc == nullptr ? launch_staged<true, 0>(p, stream) : launch_staged<false, 0>(p, stream);
 }
 

@@ -14,12 +14,12 @@ import torch
 from torch import nn
 
 from .encoder_layer import _get_activation_fn
-from .ms_deform_attn import MSDeformAttn
+from .ms_deform_attn import CacheInvalidationMixin, MSDeformAttn
 from .norm import add_layernorm, add_layernorm_supported
 from .projections import linear_3xtf32
 
 
-class DeformableCompositeTransformerDecoderLayer(nn.Module):
+class DeformableCompositeTransformerDecoderLayer(CacheInvalidationMixin, nn.Module):
     def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
         super().__init__()
         # self attention (intra: over the points of one proposal)

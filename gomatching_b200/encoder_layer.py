@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .ms_deform_attn import MSDeformAttn
+from .ms_deform_attn import CacheInvalidationMixin, MSDeformAttn
 from .norm import add_layernorm, add_layernorm_supported
 from .projections import linear_3xtf32
 
@@ -33,7 +33,7 @@ def _get_activation_fn(activation):
     raise RuntimeError(F"activation should be relu/gelu, not {activation}.")
 
 
-class DeformableTransformerEncoderLayer(nn.Module):
+class DeformableTransformerEncoderLayer(CacheInvalidationMixin, nn.Module):
     def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
         super().__init__()
         # self attention

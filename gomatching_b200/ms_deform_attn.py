@@ -24,7 +24,32 @@ from torch.nn.init import constant_, xavier_uniform_
 
 from .ms_deform_attn_func import (ms_deform_attn_forward_fused_paired, pair_value_bf16,
                                   MSDeformAttnFunction, fused_supported, ms_deform_attn_forward_fused)
+from .projections import invalidate_caches as _invalidate_projection_caches
 from .projections import linear_3xtf32
+
+
+class CacheInvalidationMixin:
+    """Weight-derived caches (TF32 splits, the merged query projection) are keyed by version counters, which in-place
+    writes through ``param.data`` do not bump.  The usual ways weights change without a new version -- loading a state
+    dict, ``.to()`` / ``.cuda()`` / ``.half()``, switching train / eval around an optimiser step -- invalidate them here;
+    anything else (EMA writes through ``.data``) must call ``invalidate_caches()``."""
+
+    def invalidate_caches(self):
+        if hasattr(self, "_qproj_cache"):
+            self._qproj_cache = None
+        _invalidate_projection_caches()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_caches()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_caches()
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode: bool = True):
+        self.invalidate_caches()
+        return super().train(mode)
 
 
 def _is_power_of_2(n):
@@ -33,7 +58,7 @@ def _is_power_of_2(n):
     return (n & (n - 1) == 0) and n != 0
 
 
-class MSDeformAttn(nn.Module):
+class MSDeformAttn(CacheInvalidationMixin, nn.Module):
     # The reference asserts sum(H*W) == Len_in on a CUDA tensor (ms_deform_attn.py:131): a device->host sync on
     # every call, 12 per frame.  Off by default; set True to get the reference's AssertionError behaviour.
     strict_shape_check = False
@@ -83,6 +108,7 @@ class MSDeformAttn(nn.Module):
         constant_(self.value_proj.bias.data, 0.)
         xavier_uniform_(self.output_proj.weight.data)
         constant_(self.output_proj.bias.data, 0.)
+        self.invalidate_caches()          # the initialisers above write through .data (no version bump)
 
     def _merged_query_projection(self):
         """[W_offsets; W_attention] (384 x 256 for DeepSolo) and the merged bias, rebuilt only when a parameter changed."""

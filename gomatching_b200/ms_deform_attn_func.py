@@ -275,7 +275,12 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     _require(grad_output.is_cuda, "grad_output must be a CUDA tensor")
     _check_im2col_step(N, im2col_step)
     _require(value.dtype == torch.float32, "msda_b200 backward is implemented for float32")
-    grad_output = grad_output.contiguous()
+    # the kernel reads fp32 everywhere: other dtypes are converted on the way in and the grads converted back
+    loc_dtype, attn_dtype = sampling_loc.dtype, attn_weight.dtype
+    sampling_loc = sampling_loc.float().contiguous()
+    attn_weight = attn_weight.float().contiguous()
+    grad_output = grad_output.float().contiguous()
+    _require(tuple(grad_output.shape) == (N, Lq, M * D), "grad_output must be (N, Lq, M*D)")
     grad_value = torch.zeros_like(value)                   # accumulated with atomics, like ms_deform_attn_cuda.cu:118
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
@@ -286,7 +291,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
             attn_weight.data_ptr(), grad_output.data_ptr(), N, S, M, D, L, Lq, P, grad_value.data_ptr(),
             grad_loc.data_ptr(), grad_attn.data_ptr(), stream)
     _native.check(rc, "ms_deform_attn_backward")
-    return [grad_value, grad_loc, grad_attn]
+    return [grad_value, grad_loc.to(loc_dtype), grad_attn.to(attn_dtype)]
 
 
 class MSDeformAttnFunction(torch.autograd.Function):

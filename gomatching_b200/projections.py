@@ -29,12 +29,21 @@ def split_weight(weight: torch.Tensor):
     w = w.contiguous()
     N, K = w.shape
     hi, lo = torch.empty_like(w), torch.empty_like(w)
-    _native.check(_native.lib().msda_b200_linear_split_weight_f32(
-        w.data_ptr(), N, K, hi.data_ptr(), lo.data_ptr(), torch.cuda.current_stream(w.device).cuda_stream),
-        "msda_b200_linear_split_weight_f32")
+    with torch.cuda.device(w.device):              # the library launches on the CURRENT device
+        _native.check(_native.lib().msda_b200_linear_split_weight_f32(
+            w.data_ptr(), N, K, hi.data_ptr(), lo.data_ptr(), torch.cuda.current_stream(w.device).cuda_stream),
+            "msda_b200_linear_split_weight_f32")
     ref = weakref.ref(weight, lambda _r, k=key: _split_cache.pop(k, None))
     _split_cache[key] = (ref, weight._version, weight.data_ptr(), hi, lo)
     return hi, lo
+
+
+def invalidate_caches() -> None:
+    """Drop every cached TF32 weight split.  The cache is keyed by the weight's identity, version counter and storage
+    pointer; an in-place write through ``param.data`` (EMA, weight-swap hooks, ``_reset_parameters``) bumps none of them, so
+    such code must call this (``MSDeformAttn`` and the drop-in layers do it from ``_load_from_state_dict``, ``_apply`` and
+    ``train``)."""
+    _split_cache.clear()
 
 
 def linear_3xtf32(x: torch.Tensor, weight: torch.Tensor, bias: "torch.Tensor | None" = None,
@@ -71,16 +80,17 @@ def linear_3xtf32(x: torch.Tensor, weight: torch.Tensor, bias: "torch.Tensor | N
         if rz.numel() != M:
             raise ValueError("row_zero must have one entry per row of x")
     b = bias.detach().contiguous() if bias is not None else None
-    if relu:
-        if rz is not None:
-            raise ValueError("linear_3xtf32: relu and row_zero cannot be combined")
-        _native.check(_native.lib().msda_b200_linear_relu_f32(
-            x2.data_ptr(), x2.stride(0), hi.data_ptr(), lo.data_ptr(), b.data_ptr() if b is not None else None,
-            M, N, K, y2.data_ptr(), y2.stride(0), torch.cuda.current_stream(x.device).cuda_stream),
-            "msda_b200_linear_relu_f32")
-        return out
-    _native.check(_native.lib().msda_b200_linear_f32(
-        x2.data_ptr(), x2.stride(0), hi.data_ptr(), lo.data_ptr(), b.data_ptr() if b is not None else None,
-        rz.data_ptr() if rz is not None else None, M, N, K, y2.data_ptr(), y2.stride(0),
-        torch.cuda.current_stream(x.device).cuda_stream), "msda_b200_linear_f32")
+    if relu and rz is not None:
+        raise ValueError("linear_3xtf32: relu and row_zero cannot be combined")
+    with torch.cuda.device(x.device):              # sm count, kernel attributes and the launch follow the current device
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        if relu:
+            _native.check(_native.lib().msda_b200_linear_relu_f32(
+                x2.data_ptr(), x2.stride(0), hi.data_ptr(), lo.data_ptr(), b.data_ptr() if b is not None else None,
+                M, N, K, y2.data_ptr(), y2.stride(0), stream), "msda_b200_linear_relu_f32")
+        else:
+            _native.check(_native.lib().msda_b200_linear_f32(
+                x2.data_ptr(), x2.stride(0), hi.data_ptr(), lo.data_ptr(), b.data_ptr() if b is not None else None,
+                rz.data_ptr() if rz is not None else None, M, N, K, y2.data_ptr(), y2.stride(0), stream),
+                "msda_b200_linear_f32")
     return out

@@ -56,6 +56,12 @@ class _FrameGraph:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.img, self.out, self.re = body()
         self.calls = _native.calls - calls0          # kernel-launching C-ABI calls of this library inside one replay
+        # The captured launches hold raw pointers to weight-derived tensors that live OUTSIDE the graph's memory pool
+        # (TF32 weight splits, merged query projections): keep them alive for as long as the graph exists.  Weights are
+        # baked in at capture time -- GoMatching's spotter is frozen; after changing them call GraphedSpotter.reset().
+        from .. import projections
+        self.keepalive = [list(projections._split_cache.values()),
+                          [m._qproj_cache for m in model.modules() if getattr(m, "_qproj_cache", None) is not None]]
 
     def replay(self, frame: torch.Tensor):
         self.frame.copy_(frame, non_blocking=True)
@@ -116,6 +122,11 @@ class GraphedSpotter:
 
     def _rescoring_head(self, query_features):
         return self.current.re.clone()
+
+    def reset(self):
+        """Forget the captured graphs (after the model's weights changed); the next frame re-captures."""
+        self.graphs.clear()
+        self.current = None
 
     def enable(self):
         if self.enabled:

@@ -681,3 +681,47 @@ def test_1080p_encoder_bit_exact_vs_oracle_and_reference_kernel():
     wd = syn.make_workload("decoder", 1080, 1920, n=1, seed=6, dist="local")
     cd = dict(value=wd.value.numpy(), shapes=wd.shapes.numpy(), lsi=wd.lsi.numpy(), loc=wd.loc.numpy(), attn=wd.attn.numpy())
     assert np.array_equal(run_core(cd).cpu().numpy(), O.forward_f32(cd["value"], cd["shapes"], cd["lsi"], cd["loc"], cd["attn"]))
+
+
+def test_tuning_variant_never_changes_results_in_the_product_build(core_cases):
+    """the staged kernel's time-attribution builds (wrong results) are compiled only with -DMSDA_DIAG."""
+    a = _encoder_workload(64, 96, 41)
+    want = O.forward_f32(a["value"], a["shapes"], a["lsi"], a["loc"], a["attn"])
+    for mode in (4, 5):
+        for variant in range(0, 6):
+            assert np.array_equal(run_core(a, dict(mode=mode, variant=variant)).cpu().numpy(), want), (mode, variant)
+
+
+def test_backward_accepts_other_dtypes_and_returns_them():
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("decoder", 96, 160, n=1, seed=2, dist="uniform")
+    v, sh, ls = w.value.cuda(), w.shapes.cuda(), w.lsi.cuda()
+    go = torch.randn(1, w.loc.shape[1], 256, device="cuda")
+    gv, gl, ga = g.ms_deform_attn_backward(v, sh, ls, w.loc.cuda(), w.attn.cuda(), go, 64)
+    gv2, gl2, ga2 = g.ms_deform_attn_backward(v, sh, ls, w.loc.cuda().double(), w.attn.cuda().double(), go.double(), 64)
+    assert gl2.dtype == torch.float64 and ga2.dtype == torch.float64
+    assert torch.allclose(gl2.float(), gl, rtol=1e-4, atol=1e-5) and torch.allclose(ga2.float(), ga, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(gv2, gv, rtol=1e-3, atol=1e-4)           # atomics: summation order differs run to run
+
+
+def test_second_gpu_in_the_same_process():
+    """kernel attributes are per device, and the projection wrappers must follow the tensor's device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import gomatching_b200 as g
+    from gomatching_b200 import synthetic as syn
+    w = syn.make_workload("encoder", 96, 160, n=1, seed=3, dist="local")
+    outs = []
+    for d in (0, 1):
+        dv = torch.device("cuda", d)
+        m = g.MSDeformAttn(256, 4, 8, 4).to(dv).eval()
+        torch.manual_seed(0)
+        for p_ in m.parameters():
+            p_.data.normal_(0, 0.05)
+        m.invalidate_caches()
+        q = torch.randn(1, w.ref.shape[1], 256, generator=torch.Generator().manual_seed(1)).to(dv)
+        src = torch.randn(1, w.value.shape[1], 256, generator=torch.Generator().manual_seed(2)).to(dv)
+        with torch.no_grad():                                     # current device stays 0 for both
+            outs.append(m(q, w.ref.to(dv), src, w.shapes.to(dv), w.lsi.to(dv)).cpu())
+    assert torch.equal(outs[0], outs[1])
