@@ -66,6 +66,7 @@ def parse():
                     help="frames per step the tracker rank spots itself (clip, N > 1); -1 = same as the others")
     ap.add_argument("--dist", default="local", choices=["local", "uniform", "oor", "center"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-multi-clip", action="store_true", help="clip, N > 1: skip the N-concurrent-clips measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sublines", action="store_true", help="skip the F=1 / 1080p / reference-kernel sub-lines")
     ap.add_argument("--unfused", action="store_true", help="op: time the core operator (loc/attn precomputed)")
@@ -604,12 +605,51 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
         res["in_pipeline"] = {"encoder_us": statistics.mean(enc_us), "decoder_us": statistics.mean(dec_us) if dec_us else None,
                               "encoder_launches": len(enc_us), "S": S, "b_alg": algorithmic_bytes(1, S, S)}
     if not args.no_e2e:
-        ms_e, info_e, _ = run(host_pool, max(3, steps // 2), host_results=True)
+        ms_e, info_e, _ = run(host_pool, steps, host_results=True)
         frame_bytes = host_pool[0].numel()
         res["e2e"] = {"value": per_step / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_step,
-                      "d2h_bytes_per_step": int(info_e["d2h"]), "ms_per_step": ms_e, "steps": max(3, steps // 2),
+                      "d2h_bytes_per_step": int(info_e["d2h"]), "ms_per_step": ms_e, "steps": steps,
                       "api": "gomatching_b200.video.ClipTracker.feed(pinned uint8 HWC frames) -> per-frame track ids on the "
                              "host (frame H2D, frame-batcher kernel, spotter, record gather, reference tracker, ids D2H)"}
+    if world > 1 and not args.no_multi_clip:
+        # N concurrent clips on N GPUs: clip c's frames are sharded over ALL ranks exactly as above and gathered to ITS
+        # tracker rank c, so every rank spots and every rank runs one clip's (sequential, unchanged) tracker.  The single
+        # clip above is bounded by one tracker (Amdahl); a dataset of clips is not.
+        cts = [ClipTracker(model, weights=[1] * world, tracker_rank=c, overlap=True, graph=False if args.no_graph else None)
+               for c in range(world)]
+        kk = [0]
+
+        def multi_round():
+            for c, ct in enumerate(cts):                       # same order on every rank: the gathers are collectives
+                for _ in range(F):
+                    frames = [None] * world
+                    frames[rank] = dev_pool[(kk[0] + c) % pool_n]
+                    kk[0] += 1
+                    ct.feed(frames)
+
+        for _ in range(max(warmup, 3)):
+            multi_round()
+        cts[rank].flush()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0 = cts[rank].association_seconds()
+        t0.record()
+        for _ in range(steps):
+            multi_round()
+        cts[rank].flush()
+        t1.record()
+        barrier()
+        ms_m = reduce_max(t0.elapsed_time(t1) / steps)
+        per_step_m = world * world * F
+        res["multi_clip"] = {"value": per_step_m / (ms_m * 1e-3), "unit": "frames/s", "clips": world, "ms_per_step": ms_m,
+                             "frames_per_step": per_step_m,
+                             "tracker_ms_per_frame": (cts[rank].association_seconds() - a0) * 1e3 / (steps * world * F),
+                             "note": "N concurrent clips, one tracker rank per clip, every clip's frames sharded over all N "
+                                     "ranks with a per-round NCCL gather to its tracker rank"}
+        for ct in cts:
+            ct.drain()
+        cts[0].close()
+        del cts
     ms_s, _, _ = run(dev_pool, max(3, steps // 2), associate=False)
     res["spotting_only"] = {"value": per_step / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
                             "note": "same loop, records gathered, association skipped: the part that shards"}
@@ -744,6 +784,7 @@ def main():
                            "rank 0; the reference's tracker on rank 0 in a worker thread" % world,
             "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "detections_per_frame": clip["detections_per_frame"],
             "score_threshold": clip["score_threshold"], "cuda_graph": clip["graph"], "spotting_only": clip["spotting_only"],
+            "multi_clip": clip.get("multi_clip"),
             "clocks": clocks, "e2e": clip.get("e2e"), "gpu_launches": clip["launches"],
             "gpu_launches_note": "kernel-launching C-ABI calls of libmsda_b200.so in the timed region, all ranks (each "
                                  "enqueues >= 1 kernel); cuDNN / cuBLAS kernels of the reference's eager code not counted",

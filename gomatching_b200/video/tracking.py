@@ -143,8 +143,13 @@ class ClipTracker:
             if not self.use_batcher:
                 raise ValueError("graph=True needs the uint8 frame path (use_batcher) on a CUDA device")
             from .spotter_graph import GraphedSpotter
-            self.spotter_graph = GraphedSpotter(model, self._ImageList, input_format)
-            self.spotter_graph.enable()
+            # one graphed spotter per model object: several ClipTrackers (concurrent clips) share its captures
+            sg = model.__dict__.get("_msda_b200_spotter_graph")
+            if sg is None:
+                sg = GraphedSpotter(model, self._ImageList, input_format)
+                model.__dict__["_msda_b200_spotter_graph"] = sg
+            self.spotter_graph = sg
+            sg.enable()
 
     # ------------------------------------------------------------------------------------------ spotting
     def _install_batcher(self):
