@@ -8,12 +8,15 @@ Workload "clip" (default; BASELINE.json metric "frames/sec (DeepSolo+LST, 1280x7
 GoMatching model -- ResNet-50 + 6+6-layer DeepSolo spotter + LSTMatcher, default-initialised and seeded, imported
 unmodified from baseline/_ref (tools/refhost) -- with the B200 operator stack installed
 (``gomatching_b200.install_into_adet``), driven by ``gomatching_b200.video.ClipTracker``: frames sharded over the
-ranks, one record gather per round to rank 0, the reference's sequential tracker (unchanged) INSIDE the timed loop,
-overlapped with the next round's spotting.  One STEP = one round = ``--frames`` 1280x720 frames per spotting rank.
+ranks, one record gather per round to the clip's tracker rank, the reference's sequential tracker (unchanged) INSIDE the
+timed loop, overlapped with the next round's spotting.  At N GPUs the job is N concurrent clips (clip c tracked on rank
+c, every clip's frames sharded over all N ranks): the tracker is sequential per clip, so clips are the axis along which
+its work stays fixed per GPU; ``single_clip`` reports ONE clip over all N GPUs (bounded by one tracker).
+One STEP = one round of every clip = ``--frames`` 1280x720 frames per rank per clip.
   value      frames/s, uint8 frames resident in HBM when the timed region starts; CUDA events; max over ranks
   e2e        same through the public API with HOST frames: pinned uint8 frame H2D per frame and the frame's track
              ids D2H inside the timed region
-  spotting_only   the same loop without the association (what scales with the GPU count; the tracker is the serial term)
+  spotting_only   one clip's loop without the association (the part that shards frame-wise)
 Workload "op" (round 1's line; also measured in every clip run as ``msda``): the MSDeformAttn calls of F = 8 frames per
 GPU, 6 encoder (Lq = S = 19160) + 6 decoder (Lq = 2500) launches per step on buffers larger than L2, fp32.
   roofline   dominant kernel of the path = the encoder-shape sampler launch; achieved = SURVEY.md s8(d) algorithmic
@@ -66,7 +69,8 @@ def parse():
                     help="frames per step the tracker rank spots itself (clip, N > 1); -1 = same as the others")
     ap.add_argument("--dist", default="local", choices=["local", "uniform", "oor", "center"])
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-multi-clip", action="store_true", help="clip, N > 1: skip the N-concurrent-clips measurement")
+    ap.add_argument("--no-multi-clip", action="store_true",
+                    help="clip, N > 1: time ONE clip over all GPUs as the headline instead of N concurrent clips")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sublines", action="store_true", help="skip the F=1 / 1080p / reference-kernel sub-lines")
     ap.add_argument("--unfused", action="store_true", help="op: time the core operator (loc/attn precomputed)")
@@ -143,6 +147,8 @@ def clip_config(args):
                     "100 point-query proposals x 25 points, d=256, 8 heads, 4 levels, 4 points + LSTMatcher tracker in the "
                     "loop), default-initialised seeded weights, 1 frame per forward" % (args.height, args.width, args.height),
         "frame": "%dx%d" % (args.width, args.height),
+        "clips": "N concurrent clips at N GPUs (weak scaling in clips: one LST-Matcher rank per clip, each clip's frames sharded "
+                 "over all N ranks); `single_clip` reports ONE clip over all N GPUs",
         "detections": ("score threshold calibrated on the first frame so that %d of the 100 queries pass (SURVEY s8d: 20-60; "
                        "default-initialised scores are flat)" % args.detections) if args.detections > 0 else "config threshold 0.3",
         "l2": "every frame's forward streams > L2 of activations (the encoder feed-forward intermediate alone is 78 MB "
@@ -528,9 +534,6 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
     from tools.refhost import loader as Lr
 
     F = args.frames or 4
-    w0 = F if (args.tracker_frames < 0 or world == 1) else args.tracker_frames
-    weights = [w0] + [F] * (world - 1)
-    per_step = sum(weights)
     cfg = Lr.build_cfg(device=str(device))
     model = Lr.build_gomatching(cfg, seed=0, b200=args.level)
     pool_n = 8
@@ -541,8 +544,6 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
     clip = Lr.synthetic_clip(pool_n, args.height, args.width, seed=11 + rank)
     host_pool = [torch.from_numpy(f).pin_memory() for f in clip]
     dev_pool = [f.to(device) for f in host_pool]
-    plan = round_plan(per_step, weights)[0]
-    mine = [(t, s) for t, r, s in plan if r == rank]
 
     def reduce_max(x):
         if world > 1:
@@ -551,50 +552,66 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
             return float(t.item())
         return x
 
-    def run(pool, n_steps, associate=True, host_results=False, graph=None):
-        """n_steps rounds after `warmup` untimed ones; returns (ms per step by CUDA events incl. the association tail,
-        tracker, kernel event log, C-ABI calls)."""
-        ct = ClipTracker(model, weights=weights, overlap=True, associate=associate, host_results=host_results,
-                         graph=False if args.no_graph else graph)
+    def run(pool, n_steps, clips=1, associate=True, host_results=False, graph=None):
+        """`clips` concurrent clips; clip c's tracker lives on rank c; every clip's round shards F frames to every rank
+        (the tracker rank of a SINGLE clip spots --tracker-frames instead).  One step = one round of every clip.  Returns
+        (ms per step by CUDA events incl. the association tail -- max over ranks, info, sampler event log)."""
+        w0 = F if (args.tracker_frames < 0 or world == 1 or clips > 1) else args.tracker_frames
+        weights = [w0] + [F] * (world - 1)
+        per_round = sum(weights)
+        mine = [(t, s) for t, r, s in round_plan(per_round, weights)[0] if r == rank]
+        cts = [ClipTracker(model, weights=weights, tracker_rank=c, overlap=True, associate=associate,
+                           host_results=host_results, graph=False if args.no_graph else graph) for c in range(clips)]
+        my = cts[rank] if rank < clips else None           # the clip this rank tracks
+        sg = cts[0].spotter_graph
         k = [0]
 
-        def one_round():
-            frames = [None] * per_step
-            for t, s in mine:
-                frames[t] = pool[(k[0] * F + s) % pool_n]
+        def one_step():
+            for c, ct in enumerate(cts):                       # same order on every rank: the gathers are collectives
+                frames = [None] * per_round
+                for t, s in mine:
+                    frames[t] = pool[(k[0] * F + s + c) % pool_n]
+                ct.feed(frames)
             k[0] += 1
-            ct.feed(frames)
+
+        def flush():
+            if my is not None:
+                my.flush()
 
         for _ in range(max(warmup, 3)):
-            one_round()
-        ct.flush()
+            one_step()
+        flush()
         barrier()
         log = []
         _native.event_log = log
-        calls0 = _native.calls + (ct.spotter_graph.replayed_calls if ct.spotter_graph else 0)
+        calls0 = _native.calls + (sg.replayed_calls if sg else 0)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0 = ct.association_seconds()
+        a0 = my.association_seconds() if my else 0.0
         t0.record()
         for _ in range(n_steps):
-            one_round()
-        ct.flush()                      # the last rounds' association is inside the timed region
+            one_step()
+        flush()                         # the last rounds' association is inside the timed region
         t1.record()
         barrier()
         _native.event_log = None
         ms = reduce_max(t0.elapsed_time(t1) / n_steps)
-        info = {"calls": _native.calls + (ct.spotter_graph.replayed_calls if ct.spotter_graph else 0) - calls0, "assoc_ms_per_frame": (ct.association_seconds() - a0) * 1e3 / (n_steps * per_step),
-                "spot_ms_per_frame": None, "d2h": sum(t.numel() * t.element_size() for t in ct.host_ids[-n_steps * per_step:]) / n_steps
-                if host_results and rank == 0 else 0}
-        ct.drain()
-        info["detections_per_frame"] = (sum(len(x) for x in ct.instances[-n_steps * per_step:]) / (n_steps * per_step)
-                                        if rank == 0 and associate and ct.instances else None)
-        info["graph"] = None if ct.spotter_graph is None else {"replays": ct.spotter_graph.replays, "failed": ct.spotter_graph.failed}
-        ct.close()
+        frames_tracked = n_steps * per_round
+        info = {"calls": _native.calls + (sg.replayed_calls if sg else 0) - calls0, "per_step": per_round * clips, "weights": weights,
+                "assoc_ms_per_frame": ((my.association_seconds() - a0) * 1e3 / frames_tracked) if my else None,
+                "d2h": (sum(t.numel() * t.element_size() for t in my.host_ids[-frames_tracked:]) / n_steps * clips)
+                if (host_results and my is not None) else 0}
+        for ct in cts:
+            ct.drain()
+        info["detections_per_frame"] = (sum(len(x) for x in my.instances[-frames_tracked:]) / frames_tracked
+                                        if my is not None and associate and my.instances else None)
+        info["graph"] = None if sg is None else {"replays": sg.replays, "failed": sg.failed}
+        cts[0].close()
         return ms, info, log
 
-    ms, info, log = run(dev_pool, steps)
-    res = {"value": per_step / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": per_step, "weights": weights,
-           "launches": info["calls"] * world, "assoc_ms_per_frame": info["assoc_ms_per_frame"], "level": args.level,
+    clips = world if (world > 1 and not args.no_multi_clip) else 1
+    ms, info, log = run(dev_pool, steps, clips=clips)
+    res = {"value": info["per_step"] / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": info["per_step"], "weights": info["weights"],
+           "clips": clips, "launches": info["calls"] * world, "assoc_ms_per_frame": info["assoc_ms_per_frame"], "level": args.level,
            "detections_per_frame": info["detections_per_frame"], "graph": info["graph"], "score_threshold": threshold}
     if not log:         # graph replay: the sampler launches are inside the graph; time them in a short eager pass of the same forward
         _, _, log = run(dev_pool, 3, associate=False, graph=False)
@@ -605,53 +622,22 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
         res["in_pipeline"] = {"encoder_us": statistics.mean(enc_us), "decoder_us": statistics.mean(dec_us) if dec_us else None,
                               "encoder_launches": len(enc_us), "S": S, "b_alg": algorithmic_bytes(1, S, S)}
     if not args.no_e2e:
-        ms_e, info_e, _ = run(host_pool, steps, host_results=True)
+        ms_e, info_e, _ = run(host_pool, steps, clips=clips, host_results=True)
         frame_bytes = host_pool[0].numel()
-        res["e2e"] = {"value": per_step / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_step,
+        res["e2e"] = {"value": info_e["per_step"] / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * info_e["per_step"],
                       "d2h_bytes_per_step": int(info_e["d2h"]), "ms_per_step": ms_e, "steps": steps,
                       "api": "gomatching_b200.video.ClipTracker.feed(pinned uint8 HWC frames) -> per-frame track ids on the "
                              "host (frame H2D, frame-batcher kernel, spotter, record gather, reference tracker, ids D2H)"}
-    if world > 1 and not args.no_multi_clip:
-        # N concurrent clips on N GPUs: clip c's frames are sharded over ALL ranks exactly as above and gathered to ITS
-        # tracker rank c, so every rank spots and every rank runs one clip's (sequential, unchanged) tracker.  The single
-        # clip above is bounded by one tracker (Amdahl); a dataset of clips is not.
-        cts = [ClipTracker(model, weights=[1] * world, tracker_rank=c, overlap=True, graph=False if args.no_graph else None)
-               for c in range(world)]
-        kk = [0]
-
-        def multi_round():
-            for c, ct in enumerate(cts):                       # same order on every rank: the gathers are collectives
-                for _ in range(F):
-                    frames = [None] * world
-                    frames[rank] = dev_pool[(kk[0] + c) % pool_n]
-                    kk[0] += 1
-                    ct.feed(frames)
-
-        for _ in range(max(warmup, 3)):
-            multi_round()
-        cts[rank].flush()
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0 = cts[rank].association_seconds()
-        t0.record()
-        for _ in range(steps):
-            multi_round()
-        cts[rank].flush()
-        t1.record()
-        barrier()
-        ms_m = reduce_max(t0.elapsed_time(t1) / steps)
-        per_step_m = world * world * F
-        res["multi_clip"] = {"value": per_step_m / (ms_m * 1e-3), "unit": "frames/s", "clips": world, "ms_per_step": ms_m,
-                             "frames_per_step": per_step_m,
-                             "tracker_ms_per_frame": (cts[rank].association_seconds() - a0) * 1e3 / (steps * world * F),
-                             "note": "N concurrent clips, one tracker rank per clip, every clip's frames sharded over all N "
-                                     "ranks with a per-round NCCL gather to its tracker rank"}
-        for ct in cts:
-            ct.drain()
-        cts[0].close()
-        del cts
-    ms_s, _, _ = run(dev_pool, max(3, steps // 2), associate=False)
-    res["spotting_only"] = {"value": per_step / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
+    if clips > 1:
+        # ONE clip over all N GPUs (BASELINE.json configs[3] read literally): one tracker for the whole job -- the Amdahl term
+        ms_1, info_1, _ = run(dev_pool, max(3, steps // 2), clips=1)
+        res["single_clip"] = {"value": info_1["per_step"] / (ms_1 * 1e-3), "unit": "frames/s", "ms_per_step": ms_1,
+                              "frames_per_step": info_1["per_step"], "round_weights": info_1["weights"],
+                              "tracker_ms_per_frame": info_1["assoc_ms_per_frame"],
+                              "note": "one clip sharded over all N GPUs, one tracker rank: bounded by the reference's sequential "
+                                      "tracker (1000 / tracker_ms_per_frame frames/s) however many GPUs spot"}
+    ms_s, info_s, _ = run(dev_pool, max(3, steps // 2), clips=1, associate=False)
+    res["spotting_only"] = {"value": info_s["per_step"] / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
                             "note": "same loop, records gathered, association skipped: the part that shards"}
     return res
 
@@ -780,11 +766,12 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded uint8 frames; reference initialisers, seeded)", "config": clip_config(args),
             "frames_per_step": clip["frames_per_step"], "round_weights": clip["weights"], "install_level": clip["level"],
-            "parallelism": "frames sharded across GPUs (dp%d), N=1 per forward; one NCCL gather of the round's records to "
-                           "rank 0; the reference's tracker on rank 0 in a worker thread" % world,
+            "clips": clip["clips"], "single_clip": clip.get("single_clip"),
+            "parallelism": "dp%d: %d concurrent clip(s), clip c tracked on rank c; every clip's frames sharded over all ranks "
+                           "(N=1 per forward), one NCCL gather of each round's records to the clip's tracker rank, the "
+                           "reference's tracker in a worker thread there" % (world, clip["clips"]),
             "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "detections_per_frame": clip["detections_per_frame"],
             "score_threshold": clip["score_threshold"], "cuda_graph": clip["graph"], "spotting_only": clip["spotting_only"],
-            "multi_clip": clip.get("multi_clip"),
             "clocks": clocks, "e2e": clip.get("e2e"), "gpu_launches": clip["launches"],
             "gpu_launches_note": "kernel-launching C-ABI calls of libmsda_b200.so in the timed region, all ranks (each "
                                  "enqueues >= 1 kernel); cuDNN / cuBLAS kernels of the reference's eager code not counted",

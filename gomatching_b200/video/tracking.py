@@ -131,6 +131,9 @@ class ClipTracker:
         if overlap and self.rank == tracker_rank:
             self._worker = _Association(self)
             self._worker.start()
+        shared = model.__dict__.get("_msda_b200_spotter_graph")
+        if shared is not None:
+            shared.disable()                  # another ClipTracker of this model enabled it: re-point after the batcher below
         if self.use_batcher:
             self._install_batcher()
         # CUDA-graph replay of the static-shape part of the spotter (video/spotter_graph.py): needs the host-free
@@ -139,6 +142,8 @@ class ClipTracker:
         tr = getattr(getattr(model, "detection_transformer", None), "transformer", None)
         if graph is None:
             graph = self.use_batcher and hasattr(tr, "_shape_tensors")
+        if not graph and shared is not None and shared.graphs is not None:
+            pass                              # stays disabled for this tracker's lifetime (eager spotting was asked for)
         if graph:
             if not self.use_batcher:
                 raise ValueError("graph=True needs the uint8 frame path (use_batcher) on a CUDA device")
