@@ -44,6 +44,7 @@ SYMBOLS = (
     "msda_b200_pair_value_bf16",
     "msda_b200_forward_paired_bf16",
     "msda_b200_forward_fused_paired_bf16",
+    "msda_b200_small_mha_f32",
 )
 
 
@@ -137,6 +138,8 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_forward_paired_bf16.argtypes = [vp] * 5 + [ci] * 7 + [vp, vp]
         L.msda_b200_forward_fused_paired_bf16.restype = ci
         L.msda_b200_forward_fused_paired_bf16.argtypes = [vp, vp, vp, vp, ci, vp, vp] + [ci] * 7 + [vp, vp]
+        L.msda_b200_small_mha_f32.restype = ci
+        L.msda_b200_small_mha_f32.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ctypes.c_longlong, ctypes.c_longlong, vp]
         L.msda_b200_shape_mismatch_epoch.restype = ci
         L.msda_b200_shape_mismatch_epoch.argtypes = []
         if L.msda_b200_abi_version() != ABI_VERSION:

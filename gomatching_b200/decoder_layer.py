@@ -4,9 +4,10 @@ The point-query decoder layer of DeepSolo: self-attention among the 25 points of
 proposals at the same point index (``attn_inter``), multi-scale deformable cross-attention into the encoder memory
 (``attn_cross`` -- the B200 ``MSDeformAttn``), and a feed-forward block.  Same constructor, sub-module and parameter
 names (reference state dicts load with ``strict=True``) and the same ``forward`` signature.  The two multi-head
-self-attentions stay ``nn.MultiheadAttention`` (library code on 2 500 tokens); at inference on fp32 CUDA tensors the
-residual + LayerNorm pairs run as one kernel (``norm.add_layernorm``) and the feed-forward GEMMs on the tcgen05
-tensor cores (``projections.linear_3xtf32``), exactly as in ``encoder_layer.py``.
+self-attentions keep their ``nn.MultiheadAttention`` parameters; at inference on fp32 CUDA tensors they run as tcgen05
+projection GEMMs around one small attention kernel (``small_mha.py``: no transposed copies, no discarded attention
+weights), the residual + LayerNorm pairs as one kernel (``norm.add_layernorm``) and the feed-forward GEMMs on the tensor
+cores (``projections.linear_3xtf32``), exactly as in ``encoder_layer.py``.
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ from .encoder_layer import _get_activation_fn
 from .ms_deform_attn import CacheInvalidationMixin, MSDeformAttn
 from .norm import add_layernorm, add_layernorm_supported
 from .projections import linear_3xtf32
+from . import small_mha
 
 
 class DeformableCompositeTransformerDecoderLayer(CacheInvalidationMixin, nn.Module):
@@ -44,6 +46,13 @@ class DeformableCompositeTransformerDecoderLayer(CacheInvalidationMixin, nn.Modu
         self.norm3 = nn.LayerNorm(d_model)
         self.tensor_core_ffn = True
         self.fused_add_norm = True
+        self.fused_self_attention = True      # attn_intra / attn_inter on this library's kernels at inference
+        self._packed_intra = small_mha.PackedProjection()
+
+    def invalidate_caches(self):
+        super().invalidate_caches()
+        if getattr(self, "_packed_intra", None) is not None:
+            self._packed_intra.key = None
 
     @staticmethod
     def with_pos_embed(tensor, pos):
@@ -80,17 +89,36 @@ class DeformableCompositeTransformerDecoderLayer(CacheInvalidationMixin, nn.Modu
                 spatial_shapes_list=None):
         # tgt, query_pos: (bs, n_q, n_pts, d_model)
         bs, n_q, n_pts, dim = tgt.shape
-        # ---- intra: sequences of n_pts points, one per (batch, proposal); nn.MultiheadAttention wants (L, B, E)
-        qk = self.with_pos_embed(tgt, query_pos).reshape(bs * n_q, n_pts, dim).transpose(0, 1)
-        val = tgt.reshape(bs * n_q, n_pts, dim).transpose(0, 1)
-        intra = self.attn_intra(qk, qk, val)[0].transpose(0, 1).reshape(bs, n_q, n_pts, dim)
-        tgt = self._add_norm(tgt, intra, self.dropout_intra, self.norm_intra)
-        # ---- inter: sequences of n_q proposals, one per (batch, point index)
-        t = tgt.transpose(1, 2)                                   # (bs, n_pts, n_q, dim)
-        seq = t.reshape(bs * n_pts, n_q, dim).transpose(0, 1)
-        inter = self.attn_inter(seq, seq, seq)[0].transpose(0, 1).reshape(bs, n_pts, n_q, dim)
-        t = self._add_norm(t.contiguous(), inter, self.dropout_inter, self.norm_inter)
-        tgt_inter = t.transpose(1, 2)                             # back to (bs, n_q, n_pts, dim)
+        fast = (self.fused_self_attention and self._inference_fast_path(tgt, self.attn_intra.in_proj_weight)
+                and tgt.is_contiguous() and small_mha.supported(self.attn_intra, tgt, n_pts)
+                and small_mha.supported(self.attn_inter, tgt, n_q))
+        if fast:
+            # tokens stay in their (batch, proposal, point) row order; the attention kernel addresses sequences by strides
+            T = bs * n_q * n_pts
+            tok = tgt.view(T, dim)
+            qk = self.with_pos_embed(tgt, query_pos).reshape(T, dim)
+            intra = small_mha.self_attention(self.attn_intra, qk, tok, bs * n_q, n_pts, n_pts, 1, self._packed_intra)
+            tgt = self._add_norm(tgt, intra.view(bs, n_q, n_pts, dim), self.dropout_intra, self.norm_intra)
+            # inter: sequence = the n_q proposals at one point index p of one image: rows (b * n_q + q) * n_pts + p
+            if bs == 1:
+                inter = small_mha.self_attention(self.attn_inter, tgt.view(T, dim), None, n_pts, n_q, 1, n_pts,
+                                                 self._packed_intra)
+            else:
+                inter = torch.cat([small_mha.self_attention(self.attn_inter, tgt[b].reshape(n_q * n_pts, dim), None, n_pts, n_q,
+                                                            1, n_pts, self._packed_intra) for b in range(bs)], 0)
+            tgt_inter = self._add_norm(tgt, inter.view(bs, n_q, n_pts, dim), self.dropout_inter, self.norm_inter)
+        else:
+            # ---- intra: sequences of n_pts points, one per (batch, proposal); nn.MultiheadAttention wants (L, B, E)
+            qk = self.with_pos_embed(tgt, query_pos).reshape(bs * n_q, n_pts, dim).transpose(0, 1)
+            val = tgt.reshape(bs * n_q, n_pts, dim).transpose(0, 1)
+            intra = self.attn_intra(qk, qk, val)[0].transpose(0, 1).reshape(bs, n_q, n_pts, dim)
+            tgt = self._add_norm(tgt, intra, self.dropout_intra, self.norm_intra)
+            # ---- inter: sequences of n_q proposals, one per (batch, point index)
+            t = tgt.transpose(1, 2)                                   # (bs, n_pts, n_q, dim)
+            seq = t.reshape(bs * n_pts, n_q, dim).transpose(0, 1)
+            inter = self.attn_inter(seq, seq, seq)[0].transpose(0, 1).reshape(bs, n_pts, n_q, dim)
+            t = self._add_norm(t.contiguous(), inter, self.dropout_inter, self.norm_inter)
+            tgt_inter = t.transpose(1, 2)                             # back to (bs, n_q, n_pts, dim)
         # ---- cross attention into the encoder memory
         if reference_points.dim() == 4:                           # one reference point per proposal: shared by its points
             ref = reference_points[:, :, None, :, :].repeat(1, 1, n_pts, 1, 1)

@@ -194,6 +194,17 @@ int msda_b200_linear_relu_f32(const float* x, int ldx, const float* w_hi, const 
  * epilogue done); NULL switches tracing off.  tools/gemm_trace.py. */
 void msda_b200_linear_set_trace(long long* buf);
 
+/* ---- attention core for the short sequences of DeepSolo's point-query decoder ---------------------------------------
+ * attn_intra (25 points of a proposal) and attn_inter (100 proposals at a point index),
+ * third_party/adet/layers/deformable_transformer.py:386-404: nn.MultiheadAttention's
+ *     out[b,i,h,:] = softmax_j((q[b,i,h,:] * head_dim^-1/2) . k[b,j,h,:]) . v[b,j,h,:]
+ * between its input and output projections (those run on msda_b200_linear_f32).  q, k, v: fp32 column slices of a
+ * projection output with row pitch ld floats (head h at columns h*head_dim ..); row of (batch b, position i) =
+ * b * batch_stride + i * seq_stride, so a strided sequence order needs no transposed copy; out likewise with pitch ldo.
+ * head_dim = 32, L <= 128. */
+int msda_b200_small_mha_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
+                            int B, int L, int H, int head_dim, long long batch_stride, long long seq_stride, void* stream);
+
 /* ---- neighbour-paired bf16 value layout: an explicit operator MODE for the bf16 configuration ---------------------
  * (BASELINE.json config 3; bar 2e-2 relative vs the fp32 reference.)  The reference has no half/bf16 path
  * (AT_DISPATCH_FLOATING_TYPES, ms_deform_attn_cuda.cu:64); this mode stores value as

@@ -166,7 +166,7 @@ def test_decoder_layer_state_dict_loads_unchanged(name):
 def test_decoder_layer_matches_the_reference_layer_output(name, fast):
     c, sd = load_dec(name)
     layer = build_dec(c, sd).cuda()
-    layer.tensor_core_ffn = layer.fused_add_norm = fast
+    layer.tensor_core_ffn = layer.fused_add_norm = layer.fused_self_attention = fast
     layer.attn_cross.tensor_core_projections = fast
     t = lambda k: torch.from_numpy(c[k]).cuda()
     mask = t("mask") if c["mask"].size else None
@@ -174,3 +174,33 @@ def test_decoder_layer_matches_the_reference_layer_output(name, fast):
         out = layer(t("tgt"), t("qpos"), t("ref"), t("src"), t("shapes"), t("lsi"), mask)
     assert out.shape == tuple(c["out"].shape)
     assert rel(out.cpu(), torch.from_numpy(c["out"])) <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,bstride,sstride", [(100, 25, 25, 1), (25, 100, 1, 25), (3, 128, 128, 1), (7, 1, 1, 7)])
+def test_small_mha_matches_nn_multihead_attention(B, L, bstride, sstride):
+    """The decoder's intra / inter self-attention on this library's kernels vs nn.MultiheadAttention in float64, with the
+    strided sequence addressing both call sites use (deformable_transformer.py:386-404)."""
+    from gomatching_b200 import small_mha
+    torch.manual_seed(B * 1000 + L)
+    mha = torch.nn.MultiheadAttention(256, 8).cuda().eval()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.1)
+        mha.out_proj.bias.normal_(0, 0.1)
+    T = B * L
+    tok = torch.randn(T, 256, device="cuda")
+    pos = torch.randn(T, 256, device="cuda")
+    rows = (torch.arange(B)[:, None] * bstride + torch.arange(L)[None, :] * sstride).cuda()       # (B, L) row of each token
+    assert sorted(rows.flatten().tolist()) == list(range(T))
+    ref64 = torch.nn.MultiheadAttention(256, 8).cuda().double().eval()
+    ref64.load_state_dict({k: v.double() for k, v in mha.state_dict().items()})
+    packed = small_mha.PackedProjection()
+    with torch.no_grad():
+        for v_tokens in (None, tok):                                  # packed q=k=v, and q=k=tok+pos with v=tok
+            qk = tok if v_tokens is None else tok + pos
+            got = small_mha.self_attention(mha, qk, v_tokens, B, L, bstride, sstride, packed)
+            q64 = qk.double()[rows].transpose(0, 1)                   # (L, B, E)
+            v64 = tok.double()[rows].transpose(0, 1)
+            want = ref64(q64, q64, v64)[0].transpose(0, 1)            # (B, L, E)
+            err = float((got.double()[rows] - want).abs().max() / want.abs().max())
+            assert err <= 2e-5, (err, v_tokens is None)
