@@ -45,6 +45,7 @@ SYMBOLS = (
     "msda_b200_forward_paired_bf16",
     "msda_b200_forward_fused_paired_bf16",
     "msda_b200_small_mha_f32",
+    "msda_b200_resample_u8_hwc",
 )
 
 
@@ -140,6 +141,8 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_forward_fused_paired_bf16.argtypes = [vp, vp, vp, vp, ci, vp, vp] + [ci] * 7 + [vp, vp]
         L.msda_b200_small_mha_f32.restype = ci
         L.msda_b200_small_mha_f32.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ctypes.c_longlong, ctypes.c_longlong, vp]
+        L.msda_b200_resample_u8_hwc.restype = ci
+        L.msda_b200_resample_u8_hwc.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp]
         L.msda_b200_shape_mismatch_epoch.restype = ci
         L.msda_b200_shape_mismatch_epoch.argtypes = []
         if L.msda_b200_abi_version() != ABI_VERSION:

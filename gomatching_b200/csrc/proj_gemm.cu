@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/msda_b200.h"
 #include "tma_common.cuh"
@@ -352,11 +353,20 @@ static int linear_impl(const float* x, int ldx, const float* w_hi, const float* 
   // N tiles of at most 256 columns, all equal and a multiple of 32 (384 -> 2 x 192)
   int n_tiles = (N + 255) / 256;
   while (N % n_tiles != 0 || (N / n_tiles) % 32 != 0) ++n_tiles;
+  const int sms = msda_b200_sm_count();
+  if (sms < 0) return sms;
+  // Small M (one 720p frame = 150 row tiles for 148 SMs): with one CTA per SM nothing overlaps that CTA's prologue and
+  // epilogue, and the 2 left-over tiles make a second wave.  Halve the N tile (down to 64 columns) until two CTAs per SM
+  // are resident, so one's epilogue runs under the other's main loop; the x tile is then read twice, from L2.
+  static const int split_n = []() { const char* e = getenv("MSDA_GEMM_SPLIT_N"); return e ? atoi(e) : 1; }();
+  if (split_n) {
+    const long long tiles_m = (M + 127) / 128;
+    while (tiles_m * n_tiles < 2LL * sms && N % (2 * n_tiles) == 0 && (N / (2 * n_tiles)) % 32 == 0 && N / (2 * n_tiles) >= 64)
+      n_tiles *= 2;
+  }
   const int BN = N / n_tiles;
 
   // two 128-row sub-tiles per CTA when there are enough rows to fill the machine that way
-  const int sms = msda_b200_sm_count();
-  if (sms < 0) return sms;
   const bool two = (long long)((M + 255) / 256) * n_tiles >= 2LL * sms && 2 * BN <= 512;
   const int block_m = two ? 256 : 128;
   int tmem_cols = 32;

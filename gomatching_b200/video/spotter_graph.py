@@ -23,6 +23,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from .batcher import batch_frames
+from .resize import resize_frames_u8, shortest_edge_size
 
 __all__ = ["GraphedSpotter"]
 
@@ -34,9 +35,13 @@ class _FrameGraph:
         dev = owner.device
         self.frame = torch.zeros((h, w, 3), dtype=torch.uint8, device=dev)
 
+        nh, nw = (h, w) if owner.test_size is None else shortest_edge_size(h, w, owner.test_size[0], owner.test_size[1])
+        self.size = (nh, nw)
+
         def body():
-            img = batch_frames(self.frame, owner.mean, owner.std, flip_channels=owner.flip)
-            images = owner.ImageList(img, [(h, w)])
+            frame = self.frame if (nh, nw) == (h, w) else resize_frames_u8(self.frame, nh, nw)      # Pillow-exact, in the graph
+            img = batch_frames(frame, owner.mean, owner.std, flip_channels=owner.flip)
+            images = owner.ImageList(img, [(nh, nw)])
             features, pos = model.backbone(images)
             out = model.detection_transformer(features, pos, model.backbone)
             re = model.roi_heads.rescoring_head(out["query_features"]) if model.with_rescore else None
@@ -79,6 +84,7 @@ class GraphedSpotter:
         cfg = model.cfg
         self.mean, self.std = list(cfg.MODEL.PIXEL_MEAN), list(cfg.MODEL.PIXEL_STD)
         self.flip = input_format == "RGB"
+        self.test_size = None                        # (MIN_SIZE_TEST, MAX_SIZE_TEST) or None: set by ClipTracker
         self.graphs: Dict[Tuple[int, int], _FrameGraph] = {}
         self.current: Optional[_FrameGraph] = None
         self.enabled = False
@@ -111,7 +117,7 @@ class GraphedSpotter:
         self.replays += 1
         self.replayed_calls += g.calls
         self.current = g
-        return self.ImageList(g.img, [hw])
+        return self.ImageList(g.img, [g.size])
 
     def _backbone(self, images):
         return None, None                            # consumed only by detection_transformer, which is replayed too

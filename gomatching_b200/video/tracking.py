@@ -99,7 +99,8 @@ class ClipTracker:
     def __init__(self, model, schema: Optional[RecordSchema] = None, weights: Optional[Sequence[int]] = None,
                  tracker_rank: int = 0, overlap: bool = True, group=None, frame_size: Optional[Tuple[int, int]] = None,
                  use_batcher: Optional[bool] = None, input_format: str = "RGB", associate: bool = True,
-                 host_results: bool = False, graph: Optional[bool] = None):
+                 host_results: bool = False, graph: Optional[bool] = None,
+                 test_size: Optional[Tuple[int, int]] = None):
         self.model = model
         self.group = group
         self.rank, self.world = _world(group)
@@ -124,6 +125,11 @@ class ClipTracker:
                                          "long_match", "short_match", "post_process")}
         self.spot_s = 0.0
         self.assoc_inline_s = 0.0
+        # (MIN_SIZE_TEST, MAX_SIZE_TEST): resize every frame on the device the way the reference's predictor does on the
+        # host (ResizeShortestEdge -> PIL bilinear, text_track_visualizer.py:318-319; video/resize.py is bit-identical);
+        # None: frames are spotted at the size they come in
+        self.test_size = test_size
+        self.original_size: Optional[Tuple[int, int]] = None
         self.associate = associate            # False: records are gathered and dropped (spotting-only measurement)
         self.host_results = host_results      # True: every frame's track ids are copied to the host as they are assigned
         self.host_ids: list = []
@@ -153,6 +159,9 @@ class ClipTracker:
             if sg is None:
                 sg = GraphedSpotter(model, self._ImageList, input_format)
                 model.__dict__["_msda_b200_spotter_graph"] = sg
+            if sg.test_size != self.test_size:
+                sg.test_size = self.test_size
+                sg.reset()
             self.spotter_graph = sg
             sg.enable()
 
@@ -161,6 +170,7 @@ class ClipTracker:
         """Replace the model's host-side float conversion + eager normalise/pad (text_track_visualizer.py:315-321,
         gom_lstmatcher.py:159-170) by the frame-batcher kernel on the uint8 frame; values are bit-identical."""
         from .batcher import batch_frames
+        from .resize import resize_frames_u8, shortest_edge_size
 
         cfg = self.model.cfg
         mean, std = list(cfg.MODEL.PIXEL_MEAN), list(cfg.MODEL.PIXEL_STD)
@@ -173,8 +183,13 @@ class ClipTracker:
                 raise ValueError("the B200 frame batcher takes uint8 (H, W, 3) frames as decoded")
             if len({tuple(f.shape) for f in frames}) != 1:
                 raise ValueError("frames of one forward must share a size")
-            batch = batch_frames(torch.stack(frames) if len(frames) > 1 else frames[0], mean, std, flip_channels=flip)
-            return ImageList(batch, [tuple(f.shape[:2]) for f in frames])
+            stack = torch.stack(frames) if len(frames) > 1 else frames[0]
+            if self.test_size is not None:
+                h, w = frames[0].shape[:2]
+                nh, nw = shortest_edge_size(h, w, self.test_size[0], self.test_size[1])
+                stack = resize_frames_u8(stack, nh, nw)
+            batch = batch_frames(stack, mean, std, flip_channels=flip)
+            return ImageList(batch, [tuple(stack.shape[-3:-1])] * len(frames))
 
         self.model.preprocess_image = preprocess_image
 
@@ -184,6 +199,8 @@ class ClipTracker:
         if self.use_batcher:
             t = frame if isinstance(frame, torch.Tensor) else torch.from_numpy(frame)
             h, w = t.shape[:2]
+            if self.original_size is None:
+                self.original_size = (int(h), int(w))
             return {"image": t.to(self.device, non_blocking=True), "height": h, "width": w, "video_id": 0}
         if isinstance(frame, dict):
             return frame
@@ -296,7 +313,8 @@ class ClipTracker:
         instances = self.instances
         if self.model.min_track_len > 0:
             instances = self.model._remove_short_track(instances)
-        size = image_size or (instances[0].image_size if instances else (0, 0))
+        # GoMBatchPredictor scales the results back to the ORIGINAL frame size (text_track_visualizer.py:317, :329)
+        size = image_size or self.original_size or (instances[0].image_size if instances else (0, 0))
         return self.model.batch_postprocess(instances, [size for _ in range(len(instances))])
 
     def association_seconds(self) -> float:

@@ -258,6 +258,17 @@ int  msda_b200_forward_f32_host(msda_b200_host_ctx_t* ctx,
 int msda_b200_frames_u8_to_chw_f32(const unsigned char* frames, int N, int H, int W, int flip_channels,
                                    const float* mean3, const float* std3, int Hp, int Wp, float* out, void* stream);
 
+/* ---- test-time frame resize, bit-identical to Pillow's 8-bit bilinear resample ---------------------------------------
+ * Replaces `self.aug.get_transform(x).apply_image(x)` (ResizeShortestEdge -> PIL.Image.resize(BILINEAR)) of the
+ * reference's predictors (gomatching/text_track_visualizer.py:283-284, :318-319).  One separable pass per call:
+ *     out = clip8((2^21 + sum_{i < count} in[first + i] * k[i]) >> 22)
+ * in: device uint8 (N, H, W, C), C in {1, 3, 4}; axis 1 = horizontal (out (N, H, out_size, C)), axis 0 = vertical
+ * (out (N, out_size, W, C)); bounds: device int32 (out_size, 2) = [first, count]; coeffs: device int32 (out_size, ksize)
+ * 22-bit fixed point -- both built exactly as Pillow's precompute_coeffs / normalize_coeffs_8bpc build them
+ * (gomatching_b200/video/resize.py).  Pillow runs the horizontal pass first. */
+int msda_b200_resample_u8_hwc(const unsigned char* in, int N, int H, int W, int C, int axis, const int* bounds,
+                              const int* coeffs, int ksize, int out_size, unsigned char* out, void* stream);
+
 /* ---- residual add + LayerNorm in one pass: out = LayerNorm(x + y) * gamma + beta ------------------------------
  * The two eager steps after every attention / feed-forward block of the transformer at inference
  * (third_party/adet/layers/deformable_transformer.py:251-252, :272-273).  x, y (may be NULL), out: (rows, C) fp32

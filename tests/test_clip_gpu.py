@@ -166,3 +166,24 @@ def test_host_free_transformer_and_graph_replay_are_bit_identical_to_eager_layer
     C.assert_identical(runs["layers"][0], runs["transformer"][0], "level transformer vs layers")
     C.assert_identical(runs["layers"][0], runs["graph"][0], "graph replay vs eager")
     assert runs["layers"][1] == runs["transformer"][1] == runs["graph"][1]
+
+
+def test_device_resize_matches_the_reference_predictor_path():
+    """The reference resizes every frame on the host (ResizeShortestEdge -> PIL bilinear) before the model sees it
+    (text_track_visualizer.py:318-322).  ClipTracker(test_size=...) does it on the device, inside the replayed graph:
+    the detections must be identical to feeding host-resized frames, and results are reported at the original size."""
+    from PIL import Image
+    from gomatching_b200.video.resize import shortest_edge_size
+    cfg = C.small_cfg(device="cuda", enc=2, dec=2)
+    frames = C.L.synthetic_clip(6, 180, 320, seed=5)
+    nh, nw = shortest_edge_size(180, 320, 250, 3000)
+    host_resized = [np.asarray(Image.fromarray(f).resize((nw, nh), Image.BILINEAR)) for f in frames]
+    model = C.L.build_gomatching(cfg, seed=0, b200="transformer")
+    runs = []
+    for fr, ts, graph in ((host_resized, None, False), (frames, (250, 3000), False), (frames, (250, 3000), True)):
+        ct = ClipTracker(model, overlap=False, graph=graph, test_size=ts)
+        ct.feed(fr)
+        runs.append(C.summarize(ct.finish(image_size=(180, 320))))
+        ct.close()
+    C.assert_identical(runs[0], runs[1], "device resize (eager) vs host PIL resize")
+    C.assert_identical(runs[0], runs[2], "device resize (graph) vs host PIL resize")
