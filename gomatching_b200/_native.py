@@ -7,7 +7,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsda_b200.so")
+# MSDA_B200_LIB: load another build of the library instead (A/B timing of kernel revisions); never built automatically
+LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "libmsda_b200.so")
 _lock = threading.Lock()
 _lib = None
 ABI_VERSION = 2      # include/msda_b200.h MSDA_B200_ABI_VERSION; bumped whenever the exported symbol list changes
@@ -79,7 +80,9 @@ def lib() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         from . import build as _build
-        if not os.path.exists(LIB_PATH) or os.environ.get("MSDA_B200_REBUILD") == "1":
+        if os.environ.get("MSDA_B200_LIB"):
+            pass
+        elif not os.path.exists(LIB_PATH) or os.environ.get("MSDA_B200_REBUILD") == "1":
             _build.build(force=os.environ.get("MSDA_B200_REBUILD") == "1")
         elif _build.have_nvcc():
             _build.build()                              # rebuilds only if a source is newer than the library

@@ -45,6 +45,7 @@ constexpr int kPlUPW = 8;                                // units per consumer w
 constexpr int kPlTH = 8, kPlTWlog2 = 4;                  // 8 x 16 level-0 queries
 constexpr int kPlL = 4, kPlP = 4, kPlLPT = 16;
 constexpr int kPlRowB = 128;
+constexpr int kPlMaxList = 160;                          // longest per-CTA item list kept in shared memory (frame-group walk)
 
 __host__ __device__ constexpr int pl_wh(int l) { return l == 0 ? 20 : l == 1 ? 16 : l == 2 ? 14 : 13; }
 __host__ __device__ constexpr int pl_ww(int l) { return l == 0 ? 28 : l == 1 ? 20 : l == 2 ? 16 : 14; }
@@ -59,6 +60,7 @@ constexpr int kPlSmem = kPlRecBytes + kPlWinBytes;
 struct PipeGeom {
   CUtensorMap lv[kPlL];
   int H[kPlL], W[kPlL], start[kPlL];
+  int group;                      // frames per group of the item walk (>= 1; >= N: one group)
 };
 
 template <int OFF> __device__ __forceinline__ uint4 pl_lds128(uint32_t a) {
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
   __shared__ int sOrg[2][NL][2];      // per item parity, per sampled level: window origin (h0, w0) chosen by the producer
 
   __shared__ int sMismatch;
+  __shared__ int sItems[kPlMaxList];
   const int M = p.M, Lq = p.Lq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 2 * kPlFrontMax * NL * 3) (&sPart[0][0][0][0])[tid] = 0;
@@ -115,11 +118,41 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
   const int ntx = (geo.W[0] + (1 << kPlTWlog2) - 1) >> kPlTWlog2, nty = (geo.H[0] + kPlTH - 1) / kPlTH;
   const int tiles = ntx * nty;
   const int total = p.N * M * tiles;                       // item = (b * M + m) * tiles + tile
-  // (A frame-by-frame split -- all CTAs inside one frame's value map at a time -- cuts the DRAM reads from 657 to 378 MB
-  // per launch but runs 11 % slower, with or without a per-head placement memory: profiles/r01_s43_*, r01_s44_*.)
-  const int per_cta = (total + gridDim.x - 1) / gridDim.x;
-  const int first = blockIdx.x * per_cta;
-  const int count = max(0, min(per_cta, total - first));
+  // One group (geo.group >= N): a CTA owns ONE contiguous run of items (same head, raster-adjacent tiles) of the whole
+  // launch.  With 8 frames in flight (157 MB of value maps > L2) that reads 657 MB from DRAM per launch, 3x the maps
+  // (profiles/r02_bench_ncu_full_summary.csv).  Frame groups: the frames are walked geo.group at a time -- inside a
+  // group every CTA owns a contiguous run, and all CTAs reach the next group together -- so only one group's maps are
+  // in flight (381 MB read).  The per-CTA item sequence is tabulated in shared memory once (sItems) so that the three
+  // roles' loops stay `for n < count`: at its 80-register cap the kernel lost 10 % to any in-loop walk arithmetic.
+  // A group needs >= ~12 items per CTA or the ragged split costs more than the re-reads (round 1's frame-by-frame
+  // split, 6.5 items per CTA, ran 11 % slower: profiles/r01_s43_*).
+  int first, count;
+  bool listed = false;
+  {
+    const int G = geo.group;
+    const int items_g = G * M * tiles, full_groups = G < p.N ? p.N / G : 0;
+    const int items_t = total - full_groups * items_g;                               // the tail group (or the whole launch)
+    const int per_g = (items_g + gridDim.x - 1) / gridDim.x, per_t = (items_t + gridDim.x - 1) / gridDim.x;
+    const int cnt_g = max(0, min(per_g, items_g - (int)blockIdx.x * per_g));
+    const int cnt_t = max(0, min(per_t, items_t - (int)blockIdx.x * per_t));
+    count = full_groups * cnt_g + cnt_t;
+    first = full_groups * items_g + (int)blockIdx.x * per_t;                          // one group: first item of the run
+    if (full_groups > 0 && count <= kPlMaxList) {
+      listed = true;
+      for (int n = tid; n < count; n += blockDim.x) {
+        const int g = cnt_g > 0 ? min(n / cnt_g, full_groups) : full_groups;
+        sItems[n] = g < full_groups ? g * items_g + (int)blockIdx.x * per_g + (n - g * cnt_g)
+                                    : first + (n - full_groups * cnt_g);
+      }
+      first = 0;
+    } else if (full_groups > 0) {                                                     // list too long: one contiguous run
+      const int per_cta = (total + gridDim.x - 1) / gridDim.x;
+      first = blockIdx.x * per_cta;
+      count = max(0, min(per_cta, total - first));
+    }
+  }
+  __syncthreads();
+  auto item_at = [&](int n) -> int { return listed ? sItems[n] : first + n; };
 
   // geometric image of tile (ty, tx) in sampled level l: top-left window corner that centres the image
   auto geo_origin = [&](int l, int ty, int tx, int& gh, int& gw) {
@@ -135,7 +168,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
     if (lane == 0) {
       int prev_m = -1, prev_gh[NL], prev_gw[NL], prev_h0[NL], prev_w0[NL];
       for (int n = 0; n < count; ++n) {
-        const int item = first + n;
+        const int item = item_at(n);
         const int tile = item % tiles, bm = item / tiles;
         const int m = bm % M, b = bm / M;
         const int ty = tile / ntx, tx = tile - ty * ntx;
@@ -219,14 +252,14 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
     ItemPos cur_it{}, nxt_it{};
     Prefetched<SPL, 1, FUSED> pf;
     if (count > 0) {
-      cur_it = decode(first);
+      cur_it = decode(item_at(0));
       locate(cur_it, f, n_valid, n_bq);
       prefetch(pf, n_bq, cur_it.m);
     }
     for (int n = 0; n < count; ++n) {
       const int buf = n & 1, j = n >> 1;
       int sh = 0, sw = 0, cnt = 0;
-      if (n + 1 < count) nxt_it = decode(first + n + 1);
+      if (n + 1 < count) nxt_it = decode(item_at(n + 1));
 #pragma unroll 1
       for (int w = f; w < kPlCons; w += kPlFront) {       // this warp's strips of the item
         const bool valid = n_valid;
@@ -294,7 +327,7 @@ __global__ void __launch_bounds__(pl_threads(FUSED), 1) msda_fwd_pipelined_kerne
   for (int n = 0; n < count; ++n) {
     bool valid;
     size_t bq;
-    const ItemPos it = decode(first + n);
+    const ItemPos it = decode(item_at(n));
     const int m = it.m, b = it.b;
     locate(it, warp, valid, bq);
     const size_t unit = bq * M + m;
@@ -403,6 +436,17 @@ int launch_forward_pipelined_f32(const FwdParams& p, const long long (*hw)[2], c
     if (fn(&geo.lv[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MSDA_E_UNSUPPORTED;
+  }
+  // frames per group: as many as keep the group's value maps well inside L2 (48 MB of the 126), but at least enough
+  // for ~12 items per CTA; p.walk = 1 (diagnostic) restores the single group of round 1
+  {
+    const long long map_bytes = (long long)p.S * px;
+    const long long tiles = ((hw[0][0] + kPlTH - 1) / kPlTH) * ((hw[0][1] + (1 << kPlTWlog2) - 1) >> kPlTWlog2);
+    long long g = (48ll << 20) / (map_bytes > 0 ? map_bytes : 1);
+    if (g < 1) g = 1;
+    while (g < p.N && g * p.M * tiles < 12ll * p.grid) ++g;
+    if (g > p.N || p.walk == 1) g = p.N;
+    geo.group = (int)g;
   }
   return p.loc == nullptr ? launch_pipelined<true>(p, geo, stream) : launch_pipelined<false>(p, geo, stream);
 }

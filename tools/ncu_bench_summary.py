@@ -46,10 +46,22 @@ def main():
             w.writerow(vals)
             rec = dict(zip([hdr[i] for i in idx], vals))
             recs.append(rec)
+        # An encoder launch (Lq = S) is the TMA window kernel plus the register-gather kernel that follows it for the
+        # coarse query levels (round 2 default), or one long register-gather kernel (round 1 / small launches).
         tmax = max(float(r["gpu__time_duration.sum"]) for r in recs)
-        for rec in recs:                                      # encoder launches (Lq = S) are the long ones
-            if float(rec["gpu__time_duration.sum"]) > 0.5 * tmax:
-                enc.append(float(rec["dram__bytes_read.sum"]) + float(rec["dram__bytes_write.sum"]))
+        dram = lambda r: float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])
+        i = 0
+        while i < len(recs):
+            rec = recs[i]
+            if "pipelined" in rec["Kernel Name"]:
+                t = dram(rec)
+                if i + 1 < len(recs) and "fast_kernel" in recs[i + 1]["Kernel Name"]:
+                    t += dram(recs[i + 1])
+                    i += 1
+                enc.append(t)
+            elif float(rec["gpu__time_duration.sum"]) > 0.5 * tmax:
+                enc.append(dram(rec))
+            i += 1
     if enc:
         tj = os.path.join(os.path.dirname(os.path.abspath(out)), "traffic.json")
         json.dump({"encoder_dram_bytes_per_launch_at_frames": {frames: sum(enc) / len(enc)},
