@@ -74,7 +74,9 @@ int plan(FwdParams& p, int elem_bytes, bool fused, const msda_b200_tuning_t* tn)
     // producer / consumer window kernel for the level-0 queries (one CTA per SM = grid / 4), 64-query linear tiles for the rest
     p.staged_levels = 1;
     p.tile_q = tq;
-    p.tile_h = 0; p.tile_w_log2 = 0;
+    // tuning tile_h / tile_w > 0: 2-D pyramid tiles for the coarse query levels on the register-gather kernel
+    p.tile_h = (tn && tn->tile_h > 0) ? tn->tile_h : 0;
+    p.tile_w_log2 = (tn && tn->tile_h > 0) ? ilog2_floor(tw < 4 ? 4 : tw) : 0;
     p.grid = sms * 4;
     return 0;
   }

@@ -461,7 +461,8 @@ int launch_forward(const FwdParams& p, cudaStream_t stream) {
       if (rc != MSDA_E_UNSUPPORTED) {
         if (rc) return rc;
         FwdParams rest = p;                               // query levels 1..3: register-gather kernel
-        rest.mode = kModeLinear;
+        rest.mode = p.tile_h > 0 ? kModePyramid : kModeLinear;     // 2-D tiles for the coarse levels when asked (tuning tile_h / tile_w)
+        rest.tile_q = rest.mode == kModePyramid ? p.tile_h * (1 << p.tile_w_log2) : p.tile_q;
         rest.q_level_begin = 1;
         rest.variant = 3;
         rest.shape_flag = lv0.shape_flag;                 // ... or every query, if the host geometry was wrong

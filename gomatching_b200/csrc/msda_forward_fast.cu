@@ -80,20 +80,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) msda_fwd_fast_kernel(const FwdP
   __syncthreads();
   const int tw_log2 = p.tile_w_log2, TH = p.tile_h;
   const bool pyramid = p.mode == kModePyramid;
+  // first query level served; the whole range if the window kernel ahead of this launch reported a shape mismatch
+  const bool all_q = p.shape_flag != nullptr && *reinterpret_cast<const volatile int*>(p.shape_flag) == p.shape_epoch;
+  const int lvl_begin = all_q ? 0 : p.q_level_begin;
   if (pyramid && tid == 0) {
     int cum = 0;
     for (int l = 0; l < NL; ++l) {
       sTileCum[l] = cum;
-      cum += ((sH[l] + TH - 1) / TH) * ((sW[l] + (1 << tw_log2) - 1) >> tw_log2);
+      if (l >= lvl_begin) cum += ((sH[l] + TH - 1) / TH) * ((sW[l] + (1 << tw_log2) - 1) >> tw_log2);
     }
     sTileCum[NL] = cum;
   }
   __syncthreads();
 
   const int cstride = M * D * EB;                   // bytes between horizontally adjacent pixels
-  // first query of the range served; the whole range if the window kernel ahead of this launch reported a shape mismatch
-  const bool all_q = p.shape_flag != nullptr && *reinterpret_cast<const volatile int*>(p.shape_flag) == p.shape_epoch;
-  const int q0 = (!pyramid && p.q_level_begin > 0 && !all_q) ? sStart[p.q_level_begin] : 0;
+  const int q0 = (!pyramid && lvl_begin > 0) ? sStart[lvl_begin] : 0;          // first query of the range served (linear tiles)
   const int tiles_per_bm = pyramid ? sTileCum[NL] : (Lq - q0 + p.tile_q - 1) / p.tile_q;
   const long long total_tiles = (long long)p.N * tiles_per_bm * M;
   const int chunks_per_warp = (p.tile_q + NW * UPW - 1) / (NW * UPW);   // warp steps per tile
