@@ -498,6 +498,36 @@ def run_op_workload(args, world, rank, device, steps, warmup, barrier, with_e2e)
     return res
 
 
+def reference_loop_on_gpu(args, device, frames=16):
+    """Context for the GPU number, baseline leg only: the reference's OWN serial loop (GoMatching.batch_inference, its
+    eager modules, its host-side float conversion) on the same B200 with the UNMODIFIED reference CUDA kernel rebuilt for
+    sm_100a behind adet._C -- what the reference delivers on this GPU without this library.  None if the kernel library
+    was not built."""
+    import torch
+    from tools.refhost import loader as Lr
+    model = Lr.build_gomatching(Lr.build_cfg(device=str(device)), seed=0)            # reference classes (un-patched)
+    if not Lr.use_reference_cuda_kernel():
+        Lr.restore_reference_classes()
+        return None
+    clip = Lr.synthetic_clip(8, args.height, args.width, seed=11)
+    inputs = Lr.frames_to_inputs([clip[i % 8] for i in range(frames + 4)])
+    if args.detections > 0:
+        Lr.calibrate_detections(model, Lr.frames_to_inputs(Lr.synthetic_clip(1, args.height, args.width, seed=1))[0], args.detections)
+    with torch.no_grad():
+        model.batch_inference(inputs[:4], 0, 0, [], Lr.new_time_cost())               # warm-up clip
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        model.batch_inference(inputs[4:], 0, 0, [], Lr.new_time_cost())
+        torch.cuda.synchronize(device)
+        sec = (time.perf_counter() - t0) / frames
+    Lr.restore_reference_classes()
+    del model
+    torch.cuda.empty_cache()
+    return {"value": 1.0 / sec, "unit": "frames/s", "ms_per_frame": sec * 1e3, "frames": frames,
+            "note": "the reference's serial loop (GoMatching.batch_inference, eager modules, host float conversion) on this "
+                    "B200 with the unmodified reference CUDA kernel rebuilt for sm_100a; wall clock around one %d-frame clip" % frames}
+
+
 def reference_cuda_kernel_us(device, dist_name, F):
     """The UNMODIFIED reference CUDA kernel rebuilt for sm_100a (oracle/_ref/libmsda_refcuda.so), same encoder-shape
     launch, same protocol -- the "kernel to beat".  Baseline leg only; None when the library was not built."""
@@ -731,6 +761,7 @@ def main():
 
     cpu = None
     ref_kernel = None
+    ref_gpu = None
     if not args.no_cpu_baseline:
         if workload == "clip":
             c = CpuClip(args)
@@ -747,6 +778,8 @@ def main():
             cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": threads, "kind": "port",
                    "sample": "median of 3: all 6 encoder + 6 decoder calls of one frame via F.grid_sample "
                              "(oracle.core_gridsample = ms_deform_attn_core_pytorch restated)"}
+        if world == 1 and workload == "clip":
+            ref_gpu = reference_loop_on_gpu(args, device)
         if world == 1 and not args.no_sublines:
             us = reference_cuda_kernel_us(device, args.dist, op["F"])
             if us is not None:
@@ -775,7 +808,7 @@ def main():
             "clocks": clocks, "e2e": clip.get("e2e"), "gpu_launches": clip["launches"],
             "gpu_launches_note": "kernel-launching C-ABI calls of libmsda_b200.so in the timed region, all ranks (each "
                                  "enqueues >= 1 kernel); cuDNN / cuBLAS kernels of the reference's eager code not counted",
-            "roofline": roofline, "cpu_baseline": cpu, "msda": msda, "msda_hbm_gbs": achieved,
+            "roofline": roofline, "cpu_baseline": cpu, "reference_on_gpu": ref_gpu, "msda": msda, "msda_hbm_gbs": achieved,
         }
     else:
         line = {

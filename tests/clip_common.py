@@ -85,29 +85,5 @@ REFCUDA = os.path.join(ROOT, "oracle", "_ref", "libmsda_refcuda.so")
 
 
 def use_reference_cuda_kernel():
-    """Route ``adet._C.ms_deform_attn_forward`` to the UNMODIFIED reference CUDA kernel (ms_deform_im2col_cuda.cuh,
-    compiled where it lies by oracle/Makefile -> oracle/_ref/libmsda_refcuda.so), with the reference host wrapper's
-    behaviour (ms_deform_attn_cuda.cu:20-80: contiguous CUDA fp32 tensors, zero-initialised output)."""
-    import ctypes
-
-    if not os.path.exists(REFCUDA):
-        return False
-    lib = ctypes.CDLL(REFCUDA)
-    lib.refcuda_msda_forward_f32.restype = ctypes.c_int
-    lib.refcuda_msda_forward_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 7 + [ctypes.c_void_p] * 2
-
-    def fwd(value, shapes, lsi, loc, attn, im2col_step):
-        assert value.is_cuda and value.dtype == torch.float32
-        value, loc, attn = value.contiguous(), loc.contiguous(), attn.contiguous()
-        N, S, M, D = value.shape
-        Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
-        out = torch.zeros(N, Lq, M * D, device=value.device)
-        rc = lib.refcuda_msda_forward_f32(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(),
-                                          attn.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(),
-                                          torch.cuda.current_stream().cuda_stream)
-        assert rc == 0
-        return out
-
-    stub = sys.modules["adet._C"]
-    stub.ms_deform_attn_forward = fwd
-    return True
+    """adet._C.ms_deform_attn_forward -> the unmodified reference CUDA kernel (tools/refhost/loader.py)."""
+    return L.use_reference_cuda_kernel(REFCUDA)

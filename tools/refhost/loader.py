@@ -129,6 +129,37 @@ def use_reference_cpu_path(stub=None, msda=None):
     stub.ms_deform_attn_backward = bwd
 
 
+def use_reference_cuda_kernel(lib_path: Optional[str] = None) -> bool:
+    """Route ``adet._C.ms_deform_attn_forward`` to the UNMODIFIED reference CUDA kernel (ms_deform_im2col_cuda.cuh compiled
+    where it lies by oracle/Makefile -> oracle/_ref/libmsda_refcuda.so), with the reference host wrapper's behaviour
+    (ms_deform_attn_cuda.cu:20-80: contiguous CUDA fp32 tensors, zero-initialised output).  Checker / baseline use only.
+    False if the library was not built."""
+    import ctypes
+
+    lib_path = lib_path or os.path.join(REPO, "oracle", "_ref", "libmsda_refcuda.so")
+    if not os.path.exists(lib_path):
+        return False
+    lib = ctypes.CDLL(lib_path)
+    lib.refcuda_msda_forward_f32.restype = ctypes.c_int
+    lib.refcuda_msda_forward_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 7 + [ctypes.c_void_p] * 2
+
+    def fwd(value, shapes, lsi, loc, attn, im2col_step):
+        assert value.is_cuda and value.dtype == torch.float32
+        value, loc, attn = value.contiguous(), loc.contiguous(), attn.contiguous()
+        N, S, M, D = value.shape
+        Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+        out = torch.zeros(N, Lq, M * D, device=value.device)
+        with torch.cuda.device(value.device):
+            rc = lib.refcuda_msda_forward_f32(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(),
+                                              attn.data_ptr(), N, S, M, D, L, Lq, P, out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        return out
+
+    sys.modules["adet._C"].ms_deform_attn_forward = fwd
+    return True
+
+
 def restore_reference_classes():
     """Undo ``gomatching_b200.install_into_adet()``'s class swaps (the reference's own modules again)."""
     ns = load_reference()
