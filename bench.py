@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (clip: 4, op: 8)")
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--config", default="GoMatching_ICDAR15",
+                    help="clip: the reference config file (configs/<name>.yaml), e.g. GoMatching_PP_DSText (BASELINE.json configs[4])")
     ap.add_argument("--level", default="transformer", choices=["op", "module", "layers", "transformer"],
                     help="install_into_adet level (clip)")
     ap.add_argument("--no-graph", action="store_true", help="clip: eager spotter instead of the CUDA-graph replay")
@@ -143,14 +145,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 def clip_config(args):
     return {
-        "workload": "clip%dp: synthetic %dx%d uint8 clip through the reference's GoMatching (ResNet-50 + DeepSolo 6+6 layers, "
-                    "100 point-query proposals x 25 points, d=256, 8 heads, 4 levels, 4 points + LSTMatcher tracker in the "
-                    "loop), default-initialised seeded weights, 1 frame per forward" % (args.height, args.width, args.height),
+        "workload": "clip%dp: synthetic %dx%d uint8 clip through the reference's GoMatching built from configs/%s.yaml "
+                    "(ResNet-50 + DeepSolo 6+6 layers, point-query proposals x 25 points, d=256, 8 heads, 4 levels, 4 points + "
+                    "the config's LST-Matcher head in the loop), default-initialised seeded weights, 1 frame per forward"
+                    % (args.height, args.width, args.height, args.config),
         "frame": "%dx%d" % (args.width, args.height),
         "clips": "N concurrent clips at N GPUs (weak scaling in clips: one LST-Matcher rank per clip, each clip's frames sharded "
                  "over all N ranks); `single_clip` reports ONE clip over all N GPUs",
-        "detections": ("score threshold calibrated on the first frame so that %d of the 100 queries pass (SURVEY s8d: 20-60; "
-                       "default-initialised scores are flat)" % args.detections) if args.detections > 0 else "config threshold 0.3",
+        "detections": ("score threshold calibrated on the first frame so that %d of the queries pass (SURVEY s8d: 20-60 at 100 "
+                       "queries; default-initialised scores are flat)" % args.detections) if args.detections > 0 else "config threshold",
         "l2": "every frame's forward streams > L2 of activations (the encoder feed-forward intermediate alone is 78 MB "
               "per layer); the op-level lines rotate buffer sets larger than L2",
     }
@@ -211,7 +214,7 @@ class CpuClip:
         torch.set_num_threads(os.cpu_count() or 1)
         self.threads = torch.get_num_threads()
         self.L = L
-        self.model = L.build_gomatching(L.build_cfg(device="cpu"), seed=0)
+        self.model = L.build_gomatching(L.build_cfg(config=args.config, device="cpu"), seed=0)
         self.inputs = L.frames_to_inputs(L.synthetic_clip(4, args.height, args.width, seed=1))
         if args.detections > 0:
             L.calibrate_detections(self.model, self.inputs[0], args.detections)
@@ -505,7 +508,7 @@ def reference_loop_on_gpu(args, device, frames=16):
     was not built."""
     import torch
     from tools.refhost import loader as Lr
-    model = Lr.build_gomatching(Lr.build_cfg(device=str(device)), seed=0)            # reference classes (un-patched)
+    model = Lr.build_gomatching(Lr.build_cfg(config=args.config, device=str(device)), seed=0)   # reference classes (un-patched)
     if not Lr.use_reference_cuda_kernel():
         Lr.restore_reference_classes()
         return None
@@ -564,7 +567,7 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
     from tools.refhost import loader as Lr
 
     F = args.frames or 4
-    cfg = Lr.build_cfg(device=str(device))
+    cfg = Lr.build_cfg(config=args.config, device=str(device))
     model = Lr.build_gomatching(cfg, seed=0, b200=args.level)
     pool_n = 8
     threshold = None

@@ -35,7 +35,7 @@ def test_reference_arm_prints_one_contract_line():
     # the GPU arm builds its config from the same function and the same arguments
     sys.path.insert(0, ROOT)
     import bench
-    ns = type("A", (), dict(height=192, width=320, detections=40))()
+    ns = type("A", (), dict(height=192, width=320, detections=40, config="GoMatching_ICDAR15"))()
     assert bench.clip_config(ns) == d["config"]
 
 

@@ -131,3 +131,22 @@ def test_sharded_ranks_give_identical_track_ids_and_metrics(model_and_clip, worl
     assert got_count == id_count
     a, b = C.mot_scores(ref, ref), C.mot_scores(got, ref)
     assert C.same_scores(a, b) and np.isfinite(a["mota"]) and np.isfinite(a["idf1"])
+
+
+def test_gomatching_pp_config_runs_through_the_same_loop():
+    """BASELINE.json configs[4] model family: GoMatching++ (configs/GoMatching_PP_DSText.yaml -- 300 queries, no rescoring
+    head, the SHA_FFN_CRSATTN matcher head).  Same ClipTracker, identical to the reference's batch_inference."""
+    torch.set_num_threads(THREADS)
+    cfg = C.L.build_cfg(config="GoMatching_PP_DSText", device="cpu", MODEL__TRANSFORMER__ENC_LAYERS=1,
+                        MODEL__TRANSFORMER__DEC_LAYERS=1)
+    model = C.L.build_gomatching(cfg, seed=0)
+    assert type(model.roi_heads).__name__ == "SHA_FFN_CRSATTN" and not model.with_rescore
+    frames = C.L.synthetic_clip(9, H, W, seed=1)
+    C.L.calibrate_detections(model, C.L.frames_to_inputs(frames[:1])[0], 60)      # the class head's prior is 0.01: nothing passes 0.5
+    ref, id_count = C.reference_loop(model, frames)
+    assert min(len(r["instances"]) for r in ref) >= 10
+    ct = ClipTracker(model, overlap=True)
+    assert ct.schema.max_instances == 300
+    ct.feed(frames)
+    C.assert_identical(C.summarize(ref), C.summarize(ct.finish()), "GoMatching++")
+    assert ct.id_count == id_count

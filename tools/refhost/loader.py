@@ -102,6 +102,7 @@ def load_reference(root: Optional[str] = None):
     use_reference_cpu_path(stub, msda)
     dt = importlib.import_module("adet.layers.deformable_transformer")
     roi = importlib.import_module("gomatching.modeling.roi_heads.lstmatcher")
+    importlib.import_module("gomatching.modeling.roi_heads.shared_ffn_crsattn")     # registers SHA_FFN_CRSATTN (GoMatching++ configs)
     meta = importlib.import_module("gomatching.modeling.meta_arch.gom_lstmatcher")
     ns = types.SimpleNamespace(root=root, msda=msda, dt=dt, roi=roi, meta=meta, C=stub,
                                original=dict(MSDeformAttn=msda.MSDeformAttn,
