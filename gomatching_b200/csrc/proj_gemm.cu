@@ -92,9 +92,21 @@ struct GemmParams {
   int relu;                      // epilogue: y = max(y, 0) after the bias (encoder FFN linear1 + activation, deformable_transformer.py:249)
   int M, N, K;
   int block_n;                   // columns per CTA (multiple of 32, <= 256)
-  int tmem_cols;                 // power of two >= block_n
+  int tmem_cols;                 // power of two >= the accumulator columns of one CTA
+  int diag;                      // -DMSDA_DIAG builds only: 1 = epilogue skips its work, 2 = splitter skips the split, 4 = no MMAs,
+                                 // 16 = epilogue converts but does not store
+  int stages;                    // persistent kernel: pipeline depth (the tile-per-CTA kernels fix it at compile time)
   long long* trace;              // optional [grid][8] clock64 stamps (MSDA_GEMM_TRACE), else nullptr
 };
+
+// measurement switches of the persistent kernel (tools/gemm_trace.py): compiled in only with -DMSDA_DIAG (build.py --diag)
+__device__ __forceinline__ int diag_on(const GemmParams& p) {
+#ifdef MSDA_DIAG
+  return p.diag;
+#else
+  return 0;
+#endif
+}
 
 // MSUB 128-row sub-tiles per CTA share every weight block: MSUB = 2 halves the bytes the TMA has to pull from L2 per
 // output row (the weights are re-streamed for every CTA tile; at MSUB = 1 the kernel is bound by that stream --
@@ -283,6 +295,255 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   }
 }
 
+// ---- persistent variant --------------------------------------------------------------------------------------------
+// One CTA per SM walks the output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (N tiles fastest, so CTAs that run
+// at the same time share x tiles in L2).  What the tile-per-CTA kernel above leaves on the table at 8 frames
+// (profiles/r01_gemm_trace.txt: main loop 98 % tensor-bound, but 3.6 k clk of prologue per tile, a 12.5 k clk epilogue
+// that overlaps nothing, and 599 tiles on 148 SMs = 5 rounds for 4.05 rounds of work) is what this one removes:
+//   * the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN <= 512 columns): the MMA warp starts tile i+1 in the other
+//     buffer while four dedicated epilogue warps drain tile i (tcgen05.ld -> +bias -> swizzled staging -> TMA store);
+//   * barrier init, TMEM allocation, tensor-map fetch and the bias load happen once per CTA; the TMA producer runs ahead
+//     across tile boundaries, so the pipeline never drains between tiles;
+//   * tiles are half the size (128 x BN), so the last round wastes half as much.
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 splitter | warps 6-9 epilogue (TMEM lane quadrant = warp & 3)
+constexpr int kPThreads = 320;
+constexpr int kPMaxStages = 6;
+constexpr int kPSlabs = 2;                   // 4 KB staging slabs per epilogue warp
+constexpr int kPBatch = 1;                   // chunks converted per proxy fence / store batch
+
+__global__ void __launch_bounds__(kPThreads, 1)
+proj_gemm_3xtf32_persistent_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
+                                   const GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int MSUB = 1;                      // two sub-tiles per CTA (as in the kernel above) never won here: the tile
+                                               // would need BN <= 128 and the MMAs of a 128-column tile read twice the
+                                               // operand bytes per flop
+  constexpr int kBlockM = kSubM * MSUB;
+  constexpr uint32_t kABytes = kSubBytes * MSUB;
+  __shared__ __align__(8) unsigned long long s_bar[3 * kPMaxStages + 4];
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.block_n, stages = p.stages;
+  const int n_tiles = p.N / BN;
+  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * n_tiles;
+  const int num_kb = p.K / kBlockK;
+  const uint32_t b_bytes = (uint32_t)BN * kBlockK * 4;
+  const uint32_t stage_bytes = 2 * kABytes + 2 * b_bytes;
+  const uint32_t acc_cols = (uint32_t)(MSUB * BN);           // columns of one accumulator buffer
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto stage_x = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
+  auto stage_xl = [&](int s) { return stage_x(s) + kABytes; };
+  auto stage_wh = [&](int s) { return stage_x(s) + 2 * kABytes; };
+  auto stage_wl = [&](int s) { return stage_wh(s) + b_bytes; };
+  const uint32_t slab_base = smem_base + (uint32_t)stages * stage_bytes;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto bar_split = [&](int s) { return bar0 + 8u * (uint32_t)(kPMaxStages + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kPMaxStages + s); };
+  auto bar_acc_full = [&](int b) { return bar0 + 8u * (uint32_t)(3 * kPMaxStages + b); };
+  auto bar_acc_empty = [&](int b) { return bar0 + 8u * (uint32_t)(3 * kPMaxStages + 2 + b); };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_y) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_split(s), 4);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  long long* trace = p.trace ? p.trace + 8 * (size_t)blockIdx.x : nullptr;
+  if (trace && tid == 0) trace[0] = clock64();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty(s), ph ^ 1u);
+          mbar_expect_tx(bar_full(s), kABytes + 2 * b_bytes);
+          tma_load_2d(stage_x(s), &tm_x, bar_full(s), kb * kBlockK, m0);
+          const size_t woff = ((size_t)kb * p.N + n0) * kBlockK;
+          bulk_load(stage_wh(s), p.w_hi + woff, b_bytes, bar_full(s));
+          bulk_load(stage_wl(s), p.w_lo + woff, b_bytes, bar_full(s));
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // One thread; the loop is kept lean on purpose: with 6 MMAs of ~125 clk per K block the ~130 dependent
+    // uniform-datapath instructions of a naive issue loop (descriptor arithmetic, two barrier polls) took about as long
+    // as the MMAs themselves (ncu: tensor pipe 71 % busy, the issuer stalled on fixed latencies, never on the MMA queue).
+    // Descriptors are therefore built once and stepped by adding (bytes >> 4) to the start-address field, and only the
+    // splitter's barrier is polled -- it completes after the stage's TMA barrier, which the splitter waited for.
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kSubM >> 4) << 24);
+      const uint64_t d0 = umma_desc_sw64(smem_base);                       // stage 0, byte 0
+      const uint64_t d_step = (uint64_t)(stage_bytes >> 4);
+      const uint64_t o_xl = (uint64_t)(kABytes >> 4), o_wh = (uint64_t)((2 * kABytes) >> 4),
+                     o_wl = (uint64_t)((2 * kABytes + b_bytes) >> 4);
+      constexpr uint64_t o_k = (uint64_t)((kUmmaK * 4) >> 4), o_sub = (uint64_t)(kSubBytes >> 4);
+      uint64_t dst = d0;
+      int s = 0, i = 0;
+      uint32_t ph = 0;
+      long long w_split = 0, w_acc = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+        const int buf = i & 1;
+        long long c0 = trace ? clock64() : 0;
+        mbar_wait(bar_acc_empty(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer
+        if (trace) w_acc += clock64() - c0;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)buf * acc_cols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (trace) c0 = clock64();
+          mbar_wait(bar_split(s), ph);
+          if (trace) w_split += clock64() - c0;
+          tc_fence_after();
+          if (!(diag_on(p) & 4)) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t wh = dst + o_wh + k * o_k, wl = dst + o_wl + k * o_k;
+#pragma unroll
+              for (int h = 0; h < MSUB; ++h) {
+                const uint64_t xh = dst + h * o_sub + k * o_k, xl = xh + o_xl;
+                const uint32_t acc = acc0 + (uint32_t)(h * BN);
+                umma_tf32(acc, xl, wh, idesc, (kb | k) ? 1u : 0u);     // small terms first
+                umma_tf32(acc, xh, wl, idesc, 1u);
+                umma_tf32(acc, xh, wh, idesc, 1u);
+              }
+            }
+          }
+          umma_commit(bar_empty(s));
+          if (kb == num_kb - 1) umma_commit(bar_acc_full(buf));
+          if (++s == stages) { s = 0; ph ^= 1u; dst = d0; } else dst += d_step;
+        }
+      }
+      if (trace) { trace[1] = 0; trace[2] = w_split; trace[3] = w_acc; trace[4] = clock64(); }
+    }
+  } else if (warp < 6) {
+    // ===================== splitter =====================
+    const int t4 = tid - 64;                         // 0..127
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full(s), ph);
+        const uint32_t xa = stage_x(s) + (uint32_t)t4 * 16u, la = stage_xl(s) + (uint32_t)t4 * 16u;
+#pragma unroll
+        for (int c = 0; c < (int)(kABytes / (128 * 16)); ++c) {
+          if (diag_on(p) & 2) break;
+          uint32_t v0, v1, v2, v3, h0, h1, h2, h3, l0, l1, l2, l3;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(xa + 2048u * c));
+          split_tf32(v0, h0, l0); split_tf32(v1, h1, l1); split_tf32(v2, h2, l2); split_tf32(v3, h3, l3);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(xa + 2048u * c), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(la + 2048u * c), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_split(s));
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const uint32_t slab0 = slab_base + (uint32_t)(warp - 6) * (uint32_t)(kPSlabs * 4096);
+    const int chunks = BN / 32;
+    int it = 0, i = 0;
+    long long w_ready = 0, busy = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1;
+      const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * BN;
+      long long c0 = trace ? clock64() : 0;
+      mbar_wait(bar_acc_full(buf), ((uint32_t)i >> 1) & 1u);
+      long long c1 = trace ? clock64() : 0;
+      tc_fence_after();
+      if (diag_on(p) & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+        continue;
+      }
+#pragma unroll 1
+      for (int h = 0; h < MSUB; ++h) {
+        const int row0 = m0 + h * kSubM + 32 * q;
+        const bool zero_row = p.row_zero != nullptr && row0 + lane < p.M && p.row_zero[row0 + lane] != 0;
+#pragma unroll 1
+        for (int c0i = 0; c0i < chunks; c0i += kPBatch, it += kPBatch) {
+          const int qn = chunks - c0i < kPBatch ? chunks - c0i : kPBatch;
+          if (it >= kPSlabs) {                       // the batch that last used these slabs must be done reading them
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPSlabs / kPBatch - 1) : "memory");
+            __syncwarp();
+          }
+#pragma unroll 1
+          for (int g = 0; g < qn; ++g) {
+            const int c = c0i + g;
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)buf * acc_cols + (uint32_t)(h * BN + c * 32), v);
+            const uint32_t slab = slab0 + (uint32_t)((it + g) % kPSlabs) * 4096u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bj = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float f[4] = {__fadd_rn(__uint_as_float(v[4 * j + 0]), bj.x), __fadd_rn(__uint_as_float(v[4 * j + 1]), bj.y),
+                            __fadd_rn(__uint_as_float(v[4 * j + 2]), bj.z), __fadd_rn(__uint_as_float(v[4 * j + 3]), bj.w)};
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[e] = f[e] < 0.0f ? 0.0f : f[e];
+              }
+              if (zero_row) f[0] = f[1] = f[2] = f[3] = 0.0f;
+              const uint32_t dst = slab + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) * 16);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+            }
+          }
+          if (h == MSUB - 1 && c0i + kPBatch >= chunks) {   // the accumulator is in registers / shared memory: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+          }
+          if (diag_on(p) & 16) continue;
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            for (int g = 0; g < qn; ++g)
+              tma_store_2d(&tm_y, slab0 + (uint32_t)((it + g) % kPSlabs) * 4096u, n0 + (c0i + g) * 32, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      if (trace) { w_ready += c1 - c0; busy += clock64() - c1; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    if (trace && tid == 192) { trace[5] = clock64(); trace[6] = w_ready; trace[7] = busy; }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // w [N][K] -> TF32 head / remainder in K-BLOCKED order [K/16][N][16], so the B tile of one K block is one contiguous
 // BN x 64-byte chunk
 __global__ void split_weight_kernel(const float* __restrict__ w, float* __restrict__ wh, float* __restrict__ wl, int N, int K) {
@@ -350,11 +611,56 @@ static int linear_impl(const float* x, int ldx, const float* w_hi, const float* 
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo) |
        reinterpret_cast<uintptr_t>(y)) & 15u)
     return MSDA_E_ALIGN;
+  const int sms = msda_b200_sm_count();
+  if (sms < 0) return sms;
+  const char* pe = getenv("MSDA_GEMM_PERSISTENT");            // 0: the tile-per-CTA kernels below (A/B measurements)
+  if (!pe || atoi(pe) != 0) {
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15u)) return MSDA_E_ALIGN;      // the epilogue reads it as float4
+    // Tile = 128 rows x BN columns, BN a multiple of 32 that divides N, 2 x BN <= 512 TMEM columns.  The widest tile
+    // is the cheapest per flop (a K block costs ~4 BN + 90 clk of MMAs but never less than the ~450 clk the
+    // TMA -> split -> MMA chain needs, and the weights are re-read once per tile), so take it whenever it still makes more
+    // tiles than SMs; otherwise everything fits one round and the narrowest tile that still does spreads it over the
+    // most SMs (tools/gemm_sweep.py, profiles/r02_gemm_persistent.txt).
+    const long long row_tiles = (M + 127) / 128;
+    int BN = 0;
+    const char* forced = getenv("MSDA_GEMM_BN");               // measurements and tests only
+    if (forced && atoi(forced) >= 32 && atoi(forced) <= 256 && atoi(forced) % 32 == 0 && N % atoi(forced) == 0) {
+      BN = atoi(forced);
+    } else {
+      for (int bn = 32; bn <= 256 && bn <= N; bn += 32)
+        if (N % bn == 0) BN = bn;                                // widest
+      if (row_tiles * (N / BN) <= sms)
+        for (int bn = 32; bn < BN; bn += 32)
+          if (N % bn == 0 && row_tiles * (N / bn) <= sms) { BN = bn; break; }
+    }
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * BN) tmem_cols <<= 1;
+    const size_t stage_bytes = 2 * (size_t)kSubBytes + 2 * (size_t)BN * kBlockK * 4;
+    const size_t slabs = (size_t)4 * kPSlabs * 4096;
+    int stages = (int)((226 * 1024 - 1024 - slabs) / stage_bytes);
+    if (stages > kPMaxStages) stages = kPMaxStages;
+    const size_t smem = stages * stage_bytes + slabs + 1024;
+    CUtensorMap tm_x, tm_y;
+    int rc;
+    if ((rc = make_map(&tm_x, x, M, K, ldx, kBlockK, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map(&tm_y, y, M, N, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    GemmParams p;
+    p.trace = g_trace;
+    p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K;
+    p.block_n = BN; p.tmem_cols = tmem_cols; p.relu = relu; p.stages = stages;
+    { const char* d = getenv("MSDA_GEMM_DIAG"); p.diag = d ? atoi(d) : 0; }
+    static msda::PerDeviceOnce configured_p;
+    if (configured_p.need())
+      cudaFuncSetAttribute(proj_gemm_3xtf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    const long long tiles = row_tiles * (N / BN);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    proj_gemm_3xtf32_persistent_kernel<<<grid, kPThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_y, p);
+    return (int)cudaGetLastError();
+  }
+
   // N tiles of at most 256 columns, all equal and a multiple of 32 (384 -> 2 x 192)
   int n_tiles = (N + 255) / 256;
   while (N % n_tiles != 0 || (N / n_tiles) % 32 != 0) ++n_tiles;
-  const int sms = msda_b200_sm_count();
-  if (sms < 0) return sms;
   // Small M (one 720p frame = 150 row tiles for 148 SMs): with one CTA per SM nothing overlaps that CTA's prologue and
   // epilogue, and the 2 left-over tiles make a second wave.  Halve the N tile (down to 64 columns) until two CTAs per SM
   // are resident, so one's epilogue runs under the other's main loop; the x tile is then read twice, from L2.
@@ -380,7 +686,7 @@ static int linear_impl(const float* x, int ldx, const float* w_hi, const float* 
 
   GemmParams p;
   p.trace = g_trace;
-  p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K; p.block_n = BN; p.tmem_cols = tmem_cols; p.relu = relu;
+  p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K; p.block_n = BN; p.tmem_cols = tmem_cols; p.relu = relu; p.stages = 0; p.diag = 0;
   const int stages = two ? 3 : 2;
   const size_t stage_bytes = 2 * (size_t)kSubBytes * (two ? 2 : 1) + 2 * (size_t)BN * kBlockK * 4;
   size_t smem = stages * stage_bytes;

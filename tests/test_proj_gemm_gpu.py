@@ -31,6 +31,31 @@ def test_linear_matches_float64(M, N, K):
     assert err <= 1e-5, err
 
 
+@pytest.mark.parametrize("env", [{"MSDA_GEMM_PERSISTENT": "0"}, {"MSDA_GEMM_BN": "32"}, {"MSDA_GEMM_BN": "64"},
+                                 {"MSDA_GEMM_BN": "128"}, {"MSDA_GEMM_BN": "256"}])
+@pytest.mark.parametrize("M,N,K,relu", [(19160, 256, 256, False), (40000, 1024, 256, True), (2500, 256, 1024, False)])
+def test_every_tile_shape_and_the_tile_per_cta_kernels(monkeypatch, env, M, N, K, relu):
+    """The persistent kernel's tile width is a heuristic (and MSDA_GEMM_PERSISTENT=0 selects the round-1 kernels that the
+    A/B numbers in DESIGN.md are measured against): every choice must give the same fp32-grade result, including many
+    tiles per CTA (both TMEM accumulator buffers and every ring slot reused many times)."""
+    from gomatching_b200.projections import linear_3xtf32
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g, device="cuda") * 2.0
+    w = torch.randn(N, K, generator=g, device="cuda") / K ** 0.5
+    b = torch.randn(N, generator=g, device="cuda")
+    rz = None if relu else torch.rand(M, generator=g, device="cuda") < 0.1
+    y = linear_3xtf32(x, w, b, rz, relu=relu)
+    ref = _ref(x, w, b, rz)
+    if relu:
+        ref = ref.clamp(min=0)
+    err = float((y.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-5, err
+    if rz is not None:
+        assert bool((y[rz] == 0).all())
+
+
 def test_row_zero_bias_none_and_pitched_views():
     from gomatching_b200.projections import linear_3xtf32
     g = torch.Generator(device="cuda").manual_seed(5)
