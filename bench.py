@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--config", default="GoMatching_ICDAR15",
                     help="clip: the reference config file (configs/<name>.yaml), e.g. GoMatching_PP_DSText (BASELINE.json configs[4])")
-    ap.add_argument("--level", default="transformer", choices=["op", "module", "layers", "transformer"],
+    ap.add_argument("--level", default="heads", choices=["op", "module", "layers", "transformer", "heads"],
                     help="install_into_adet level (clip)")
     ap.add_argument("--no-graph", action="store_true", help="clip: eager spotter instead of the CUDA-graph replay")
     ap.add_argument("--detections", type=int, default=40,

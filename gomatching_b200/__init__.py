@@ -10,6 +10,7 @@ Public surface (mirrors third_party/adet/layers/ms_deform_attn.py of the referen
     DeformableTransformerEncoderLayer  encoder layer drop-in (sampler + tensor-core feed-forward block)
     DeformableCompositeTransformerDecoderLayer  point-query decoder layer drop-in
     install_into_adet            monkey-patch the reference's import sites
+    use_tensor_core_linears / accelerate_spotter   switch a built model's remaining nn.Linear layers to the tcgen05 GEMM
 """
 from .ms_deform_attn_func import (MSDeformAttnFunction, _MSDeformAttnFunction, fused_supported, locations_softmax,
                                   ms_deform_attn_backward, ms_deform_attn_forward, ms_deform_attn_forward_fused,
@@ -18,13 +19,14 @@ from .ms_deform_attn_func import (MSDeformAttnFunction, _MSDeformAttnFunction, f
 from .ms_deform_attn import MSDeformAttn
 from .encoder_layer import DeformableTransformerEncoderLayer
 from .decoder_layer import DeformableCompositeTransformerDecoderLayer
+from .projections import TensorCoreLinear, use_tensor_core_linears
 
 __all__ = [
     "MSDeformAttn", "MSDeformAttnFunction", "_MSDeformAttnFunction", "ms_deform_attn_forward",
     "ms_deform_attn_backward", "ms_deform_attn_forward_fused", "fused_supported", "sample_index",
     "locations_softmax", "install_into_adet", "pair_value_bf16", "ms_deform_attn_forward_paired",
     "ms_deform_attn_forward_fused_paired", "DeformableTransformerEncoderLayer",
-    "DeformableCompositeTransformerDecoderLayer",
+    "DeformableCompositeTransformerDecoderLayer", "TensorCoreLinear", "use_tensor_core_linears", "accelerate_spotter",
 ]
 
 
@@ -43,13 +45,19 @@ def install_into_adet(level: str = "layers"):
                 of the reference's own classes whose forwards never touch the host (transformer_dropin.py): same
                 arithmetic, bit-identical results, CUDA-graph capturable, and the level geometry reaches the TMA window
                 kernel as Python ints.
+      "heads"   the same class bindings as "transformer"; the caller then runs :func:`accelerate_spotter` on the built
+                model, which moves the spotter's remaining ``nn.Linear`` layers (proposal MLPs over all encoder tokens,
+                decoder reference-point / control-point MLPs, prediction and rescoring heads) to the tensor-core GEMM
+                (fp32-grade, not bit-identical to cuBLAS).
     Call after ``adet`` is importable and BEFORE the model is constructed; modules that are not imported yet are
     skipped."""
     import sys
     import types
 
-    if level not in ("op", "module", "layers", "transformer"):
-        raise ValueError("level must be 'op', 'module', 'layers' or 'transformer', got %r" % (level,))
+    if level not in ("op", "module", "layers", "transformer", "heads"):
+        raise ValueError("level must be 'op', 'module', 'layers', 'transformer' or 'heads', got %r" % (level,))
+    if level == "heads":
+        level = "transformer"
     c = sys.modules.get("adet._C")
     if c is None:
         c = types.ModuleType("adet._C")
@@ -89,3 +97,15 @@ def install_into_adet(level: str = "layers"):
                 if mod is not None and hasattr(mod, "DeformableTransformer"):
                     mod.DeformableTransformer = new_t
     return c
+
+
+def accelerate_spotter(model) -> int:
+    """Level "heads": re-class the plain ``nn.Linear`` layers of a built GoMatching model's frozen spotter --
+    ``model.detection_transformer`` (gom_lstmatcher.py:53) and, if present, ``model.roi_heads.rescoring_head`` (:60-66) --
+    to :class:`TensorCoreLinear`.  The tracker's association head is left alone: it runs verbatim.  Returns the number of
+    layers switched."""
+    n = use_tensor_core_linears(model.detection_transformer)
+    head = getattr(getattr(model, "roi_heads", None), "rescoring_head", None)
+    if head is not None and getattr(model, "with_rescore", True):
+        n += use_tensor_core_linears(head)
+    return n

@@ -80,6 +80,8 @@ def linear_3xtf32(x: torch.Tensor, weight: torch.Tensor, bias: "torch.Tensor | N
         if rz.numel() != M:
             raise ValueError("row_zero must have one entry per row of x")
     b = bias.detach().contiguous() if bias is not None else None
+    if b is not None and b.data_ptr() % 16 != 0:   # the epilogue reads the bias as float4
+        b = b.clone()
     if relu and rz is not None:
         raise ValueError("linear_3xtf32: relu and row_zero cannot be combined")
     with torch.cuda.device(x.device):              # sm count, kernel attributes and the launch follow the current device
@@ -94,3 +96,31 @@ def linear_3xtf32(x: torch.Tensor, weight: torch.Tensor, bias: "torch.Tensor | N
                 rz.data_ptr() if rz is not None else None, M, N, K, y2.data_ptr(), y2.stride(0), stream),
                 "msda_b200_linear_f32")
     return out
+
+
+class TensorCoreLinear(torch.nn.Linear):
+    """``nn.Linear`` whose CUDA fp32 inference forward runs on the 3xTF32 tcgen05 GEMM.  Same parameters, same state dict,
+    same result to fp32 rounding (<= 1e-5 of max|y| against float64, tests/test_proj_gemm_gpu.py); everything the kernel
+    does not take -- CPU tensors, other dtypes, ``out_features % 32`` or ``in_features % 16`` non-zero (the 256 -> 1 / 2 /
+    8 heads), a forward that needs gradients -- is ``nn.Linear`` itself."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32 and x.numel() > 0
+                and self.out_features % 32 == 0 and self.in_features % 16 == 0 and self.out_features <= 1024
+                and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
+            return linear_3xtf32(x, self.weight, self.bias)
+        return torch.nn.functional.linear(x, self.weight, self.bias)
+
+
+def use_tensor_core_linears(module: torch.nn.Module) -> int:
+    """Re-class every plain ``nn.Linear`` under ``module`` to ``TensorCoreLinear`` in place (parameters untouched) and
+    return how many were switched.  Meant for the spotter's frozen detection transformer and rescoring head -- the
+    proposal MLPs over all S encoder tokens (deformable_transformer.py:137,182-183), the decoder's reference-point and
+    control-point MLPs (:476-486) and the prediction heads (detection_transformer_wobackbone.py:199-216) -- which the
+    reference runs as fp32 SIMT cuBLAS GEMMs."""
+    n = 0
+    for m in module.modules():
+        if type(m) is torch.nn.Linear:
+            m.__class__ = TensorCoreLinear
+            n += 1
+    return n

@@ -66,10 +66,10 @@ def _spotter_outputs(model, frame):
     return {k: v.double() for k, v in out.items() if v is not None}
 
 
-@pytest.mark.parametrize("level", ["module", "layers"])
+@pytest.mark.parametrize("level", ["module", "layers", "heads"])
 def test_dropin_module_and_layers_stay_within_tolerance(reference_run, level):
-    """Levels "module" / "layers" (fused glue, tensor-core projections, fused add+LayerNorm)
-    change the summation order of the dense projections, so the spotter's outputs move at fp32 rounding level
+    """Levels "module" / "layers" / "heads" (fused glue, tensor-core projections, fused
+    add+LayerNorm; "heads": every remaining nn.Linear of the spotter on the tensor-core GEMM) change the summation order of the dense projections, so the spotter's outputs move at fp32 rounding level
     (bar: 1e-4 of max|ref|, the operator's fp32 bar).  Discrete decisions downstream (NMS order, Hungarian) can then
     flip at near-ties -- which a default-initialised model has in abundance (near-duplicate boxes) -- so identity of
     track IDs is asserted for level "op" only; here the raw outputs are checked, and the clip-level effect is
@@ -81,6 +81,10 @@ def test_dropin_module_and_layers_stay_within_tolerance(reference_run, level):
     want = [_spotter_outputs(ref_model, f) for f in inputs]
     del ref_model
     model = C.L.build_gomatching(cfg, seed=0, b200=level, state_dict=sd)
+    if level == "heads":
+        from gomatching_b200 import TensorCoreLinear
+        assert sum(isinstance(m, TensorCoreLinear) for m in model.detection_transformer.modules()) >= 10
+        assert not any(isinstance(m, TensorCoreLinear) for m in model.roi_heads.asso_head.modules()), "the tracker runs verbatim"
     for f, w in zip(inputs, want):
         got = _spotter_outputs(model, f)
         for k in w:
@@ -152,7 +156,8 @@ def test_host_free_transformer_and_graph_replay_are_bit_identical_to_eager_layer
     frames = C.L.synthetic_clip(12, H, W, seed=1)
     runs = {}
     sd = None
-    for name, level, graph in (("layers", "layers", False), ("transformer", "transformer", False), ("graph", "transformer", True)):
+    for name, level, graph in (("layers", "layers", False), ("transformer", "transformer", False), ("graph", "transformer", True),
+                               ("heads", "heads", False), ("heads_graph", "heads", True)):
         model = C.L.build_gomatching(cfg, seed=0, b200=level, state_dict=sd)
         if sd is None:
             sd = {k: v.clone() for k, v in model.state_dict().items()}
@@ -165,7 +170,9 @@ def test_host_free_transformer_and_graph_replay_are_bit_identical_to_eager_layer
         del model, ct
     C.assert_identical(runs["layers"][0], runs["transformer"][0], "level transformer vs layers")
     C.assert_identical(runs["layers"][0], runs["graph"][0], "graph replay vs eager")
+    C.assert_identical(runs["heads"][0], runs["heads_graph"][0], "level heads: graph replay vs eager")
     assert runs["layers"][1] == runs["transformer"][1] == runs["graph"][1]
+    assert runs["heads"][1] == runs["heads_graph"][1]
 
 
 def test_device_resize_matches_the_reference_predictor_path():

@@ -87,3 +87,31 @@ def test_host_free_transformer_with_padding_masks():
                 assert torch.equal(want[k], got[k]), k
     finally:
         C.L.restore_reference_classes()
+
+
+def test_tensor_core_linears_keep_parameters_and_cpu_behaviour():
+    """Level "heads" re-classes the spotter's nn.Linear layers in place: same parameters and state-dict keys, the
+    tracker's association head untouched, and anything the kernel does not take (here: CPU tensors) is nn.Linear itself,
+    so the whole clip still reproduces the reference bit for bit on the host."""
+    import gomatching_b200
+    from gomatching_b200 import TensorCoreLinear
+    torch.set_num_threads(2)
+    cfg = C.small_cfg(enc=1, dec=1)
+    model = C.L.build_gomatching(cfg, seed=0)
+    keys = list(model.state_dict().keys())
+    frames = C.L.synthetic_clip(4, 128, 192, seed=3)
+    ref, id_count = C.reference_loop(model, frames)
+    n = gomatching_b200.accelerate_spotter(model)
+    assert n >= 10 and n == sum(isinstance(m, TensorCoreLinear) for m in model.modules())
+    assert list(model.state_dict().keys()) == keys
+    assert not any(isinstance(m, TensorCoreLinear) for m in model.roi_heads.asso_head.modules())
+    assert gomatching_b200.accelerate_spotter(model) == 0                       # idempotent
+    out, id_count2 = C.reference_loop(model, frames)
+    C.assert_identical(C.summarize(ref), C.summarize(out), "TensorCoreLinear on the host")
+    assert id_count2 == id_count
+    lin = TensorCoreLinear(48, 64)
+    x = torch.randn(5, 48, requires_grad=True)
+    lin(x).sum().backward()                                                     # gradients: the nn.Linear path
+    assert x.grad is not None and lin.weight.grad is not None
+    with pytest.raises(ValueError):
+        gomatching_b200.install_into_adet(level="everything")

@@ -231,7 +231,7 @@ def build_cfg(config: str = "GoMatching_ICDAR15", device: str = "cpu", **overrid
 # ----------------------------------------------------------------------------------------------- model
 def build_gomatching(cfg, seed: int = 0, b200=False, state_dict=None):
     """Instantiate the reference's GoMatching with its own initialisers (seeded).  ``b200`` (True = "layers", or
-    "op" / "module") installs the B200 operator / module / layers first (gomatching_b200.install_into_adet) so
+    "op" / "module" / "transformer" / "heads") installs the B200 operator / module / layers first (gomatching_b200.install_into_adet) so
     DeepSolo's encoder and decoder are built from them; pass ``state_dict`` of a reference-built model to get identical weights."""
     load_reference()
     restore_reference_classes()
@@ -245,6 +245,8 @@ def build_gomatching(cfg, seed: int = 0, b200=False, state_dict=None):
     model.eval()
     for p in model.parameters():
         p.requires_grad_(False)
+    if b200 == "heads":
+        gomatching_b200.accelerate_spotter(model)
     return model
 
 
