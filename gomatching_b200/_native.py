@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "libmsda_b200.so")
 _lock = threading.Lock()
 _lib = None
-ABI_VERSION = 2      # include/msda_b200.h MSDA_B200_ABI_VERSION; bumped whenever the exported symbol list changes
+ABI_VERSION = 3      # include/msda_b200.h MSDA_B200_ABI_VERSION; bumped whenever the exported symbol list changes
 
 # every symbol include/msda_b200.h declares; tests/test_abi.py checks header <-> list <-> .so agree
 SYMBOLS = (
@@ -46,6 +46,8 @@ SYMBOLS = (
     "msda_b200_forward_paired_bf16",
     "msda_b200_forward_fused_paired_bf16",
     "msda_b200_small_mha_f32",
+    "msda_b200_point_pos_embed_f32",
+    "msda_b200_refine_points_f32",
     "msda_b200_resample_u8_hwc",
 )
 
@@ -144,6 +146,10 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_forward_fused_paired_bf16.argtypes = [vp, vp, vp, vp, ci, vp, vp] + [ci] * 7 + [vp, vp]
         L.msda_b200_small_mha_f32.restype = ci
         L.msda_b200_small_mha_f32.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ctypes.c_longlong, ctypes.c_longlong, vp]
+        L.msda_b200_point_pos_embed_f32.restype = ci
+        L.msda_b200_point_pos_embed_f32.argtypes = [vp, vp, ci, vp, ctypes.c_longlong, ci, ci, vp, vp]
+        L.msda_b200_refine_points_f32.restype = ci
+        L.msda_b200_refine_points_f32.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp, vp]
         L.msda_b200_resample_u8_hwc.restype = ci
         L.msda_b200_resample_u8_hwc.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp]
         L.msda_b200_shape_mismatch_epoch.restype = ci

@@ -8,8 +8,9 @@
 //     out[b, i, h, :] = softmax_j( (q[b,i,h,:] * d^-1/2) . k[b,j,h,:] ) . v[b,j,h,:]
 // q, k, v are COLUMN SLICES of the packed projection output (row pitch ld floats), rows addressed as
 // row(b, i) = b * batch_stride + i * seq_stride -- so the "inter" attention reads the (proposal, point) row order it is
-// given and needs no transposed copy.  One CTA per (batch, head): K and V of the sequence live in shared memory
-// (rows padded to 33 floats), a warp owns a query row at a time: lanes = keys for the scores and the softmax (shuffle
+// given and needs no transposed copy.  One CTA per (batch, head, chunk of query rows): K and V of the sequence live in
+// shared memory (rows padded to 33 floats; the 100-key sequences are split into row chunks so that ~6 CTAs per SM are in
+// flight instead of 200 long serial ones), a warp owns a query row at a time: lanes = keys for the scores and the softmax (shuffle
 // reductions, exp via expf like torch), lanes = channels for the weighted sum.  fp32 throughout; same operation order as
 // the reference up to the summation order inside the two dot products.
 #include <cuda_runtime.h>
@@ -41,7 +42,9 @@ __global__ void __launch_bounds__(128) small_mha_kernel(const float* __restrict_
     sV[j * kPad + c] = v[r];
   }
   __syncthreads();
-  for (int i = warp; i < L; i += 4) {
+  const int rows_per_cta = (L + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int i_begin = blockIdx.y * rows_per_cta, i_end = min(L, i_begin + rows_per_cta);
+  for (int i = i_begin + warp; i < i_end; i += 4) {
     const long long r = row0 + (long long)i * seq_stride;
     sQ[warp][lane] = __fmul_rn(q[r * ld + h * kHd + lane], scale);          // q * d^-1/2 first, like the reference
     __syncwarp();
@@ -74,9 +77,16 @@ __global__ void __launch_bounds__(128) small_mha_kernel(const float* __restrict_
       if (j < L) sP[warp][j] = __fdiv_rn(s[t], sum);
     }
     __syncwarp();
-    float o = 0.0f;
-    for (int j = 0; j < L; ++j) o = __fmaf_rn(sP[warp][j], sV[j * kPad + lane], o);
-    out[r * ldo + h * kHd + lane] = o;
+    float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;       // four independent chains: the sum is latency-bound otherwise
+    int j = 0;
+    for (; j + 3 < L; j += 4) {
+      o0 = __fmaf_rn(sP[warp][j], sV[j * kPad + lane], o0);
+      o1 = __fmaf_rn(sP[warp][j + 1], sV[(j + 1) * kPad + lane], o1);
+      o2 = __fmaf_rn(sP[warp][j + 2], sV[(j + 2) * kPad + lane], o2);
+      o3 = __fmaf_rn(sP[warp][j + 3], sV[(j + 3) * kPad + lane], o3);
+    }
+    for (; j < L; ++j) o0 = __fmaf_rn(sP[warp][j], sV[j * kPad + lane], o0);
+    out[r * ldo + h * kHd + lane] = __fadd_rn(__fadd_rn(o0, o1), __fadd_rn(o2, o3));
     __syncwarp();
   }
 }
@@ -91,6 +101,11 @@ extern "C" int msda_b200_small_mha_f32(const float* q, const float* k, const flo
   if (B <= 0 || L <= 0 || H <= 0 || ld < H * head_dim || ldo < H * head_dim) return MSDA_E_DIMS;
   if (head_dim != kHd || L > kMaxL) return MSDA_E_UNSUPPORTED;
   const float scale = 0.17677669529663687f;          // float(32 ** -0.5), the value torch multiplies q by
-  small_mha_kernel<<<B * H, 128, 0, (cudaStream_t)stream>>>(q, k, v, ld, out, ldo, L, H, batch_stride, seq_stride, scale);
+  const int sms = msda_b200_sm_count();
+  if (sms < 0) return sms;
+  int chunks = (6 * sms) / (B * H);                  // ~6 resident CTAs per SM
+  if (chunks > (L + 3) / 4) chunks = (L + 3) / 4;    // at least one row per warp
+  if (chunks < 1) chunks = 1;
+  small_mha_kernel<<<dim3(B * H, chunks), 128, 0, (cudaStream_t)stream>>>(q, k, v, ld, out, ldo, L, H, batch_stride, seq_stride, scale);
   return (int)cudaGetLastError();
 }

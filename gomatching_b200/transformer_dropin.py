@@ -22,6 +22,8 @@ from __future__ import annotations
 
 import torch
 
+from . import decoder_glue
+
 __all__ = ["make_dropin_classes"]
 
 
@@ -184,16 +186,24 @@ def make_dropin_classes(dt_module):
             output = tgt
             assert reference_points.shape[-1] == 2
             intermediate, intermediate_reference_points = [], []
+            # one-launch glue (decoder_glue.py, bit-identical to the eager functions) on CUDA fp32
+            fused = decoder_glue.supported(tgt, reference_points, valid_ratios) and not torch.is_grad_enabled()
             for lid, layer in enumerate(dec.layers):
                 reference_points_input = reference_points[:, :, :, None] * valid_ratios[:, None, None]
-                query_pos = dt_module.gen_point_pos_embed(reference_points_input[:, :, :, 0, :], dec.d_model, dec.temp)
+                if fused:
+                    query_pos = decoder_glue.point_pos_embed(reference_points, valid_ratios, dec.d_model, dec.temp)
+                else:
+                    query_pos = dt_module.gen_point_pos_embed(reference_points_input[:, :, :, 0, :], dec.d_model, dec.temp)
                 query_pos = dec.ref_point_head(query_pos)
                 output = layer(output, query_pos, reference_points_input, src, spatial_shapes, level_start_index,
                                padding_mask, spatial_shapes_list=shapes_list)
                 if dec.ctrl_point_coord is not None:
                     tmp = dec.ctrl_point_coord[lid](output)
-                    new_reference_points = tmp + dt_module.inverse_sigmoid(reference_points)
-                    reference_points = new_reference_points.sigmoid().detach()
+                    if fused:
+                        reference_points = decoder_glue.refine_points(tmp, reference_points)
+                    else:
+                        new_reference_points = tmp + dt_module.inverse_sigmoid(reference_points)
+                        reference_points = new_reference_points.sigmoid().detach()
                 if dec.return_intermediate:
                     intermediate.append(output)
                     intermediate_reference_points.append(reference_points)

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 2
+#define MSDA_B200_ABI_VERSION 3
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define MSDA_E_NULLPTR   (-1)   /* a required pointer is NULL                                   */
@@ -204,6 +204,20 @@ void msda_b200_linear_set_trace(long long* buf);
  * head_dim = 32, L <= 128. */
 int msda_b200_small_mha_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
                             int B, int L, int H, int head_dim, long long batch_stride, long long seq_stride, void* stream);
+
+/* ---- elementwise glue of the point-query decoder, one launch each -------------------------------------------------
+ * point_pos_embed: gen_point_pos_embed(reference_points_input[:, :, :, 0, :], d_model, temp)
+ *   (third_party/adet/modeling/model/utils.py:24-37, called at deformable_transformer.py:477):
+ *     out[p][xy * half_dim + i] = (i odd ? cos : sin)( ref[p][xy] * ratio[b(p)][xy] * 2 pi / dim_t[i] )
+ *   ref: (points, 2) fp32; ratio: valid ratios of level 0, element [b * ratio_stride + xy], b = p / points_per_batch, or
+ *   NULL (= 1); dim_t: (half_dim) fp32 = temp ** (2 * (i // 2) / half_dim) as the caller's framework computes it; out:
+ *   (points, 2 * half_dim).
+ * refine_points: (tmp + inverse_sigmoid(ref)).sigmoid() over n fp32 elements (deformable_transformer.py:483-486,
+ *   adet/utils/misc.py:115-119; eps = 1e-5 there).
+ * Both repeat the eager fp32 operation order and are bit-identical to it. */
+int msda_b200_point_pos_embed_f32(const float* ref, const float* ratio, int ratio_stride, const float* dim_t, long long points,
+                                  int points_per_batch, int half_dim, float* out, void* stream);
+int msda_b200_refine_points_f32(const float* tmp, const float* ref, long long n, float eps, float* out, void* stream);
 
 /* ---- neighbour-paired bf16 value layout: an explicit operator MODE for the bf16 configuration ---------------------
  * (BASELINE.json config 3; bar 2e-2 relative vs the fp32 reference.)  The reference has no half/bf16 path

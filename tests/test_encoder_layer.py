@@ -204,3 +204,43 @@ def test_small_mha_matches_nn_multihead_attention(B, L, bstride, sstride):
             want = ref64(q64, q64, v64)[0].transpose(0, 1)            # (B, L, E)
             err = float((got.double()[rows] - want).abs().max() / want.abs().max())
             assert err <= 2e-5, (err, v_tokens is None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs,nq,npts,levels", [(1, 100, 25, 4), (2, 300, 25, 4), (3, 7, 5, 1)])
+def test_decoder_glue_is_bit_identical_to_the_eager_expressions(bs, nq, npts, levels):
+    """csrc/decoder_glue.cu against the eager tensor expressions it replaces -- the positional embedding of the current
+    reference points (adet/modeling/model/utils.py:24-37 on reference_points * valid_ratios, level 0) and the
+    reference-point refinement (deformable_transformer.py:483-486 with adet/utils/misc.py:115-119): every bit equal,
+    including points outside [0, 1], exact 0 / 1, and NaN."""
+    import math
+    from gomatching_b200 import decoder_glue
+    g = torch.Generator(device="cuda").manual_seed(bs * 100 + nq)
+    ref = torch.rand(bs, nq, npts, 2, generator=g, device="cuda") * 1.4 - 0.2
+    ref.view(-1)[:6] = torch.tensor([0.0, 1.0, -0.0, 1e-6, 1.0 - 1e-6, 0.5], device="cuda")
+    vr = torch.rand(bs, levels, 2, generator=g, device="cuda") * 0.5 + 0.5
+    d_model, temp = 256, 10000
+    got = decoder_glue.point_pos_embed(ref, vr, d_model, temp)
+    pts = (ref[:, :, :, None] * vr[:, None, None])[:, :, :, 0, :]
+    dim = d_model // 2
+    dim_t = torch.arange(dim, dtype=torch.float32, device="cuda")
+    dim_t = temp ** (2 * torch.div(dim_t, 2, rounding_mode='trunc') / dim)
+    px = (pts[:, :, :, 0] * (2 * math.pi))[:, :, :, None] / dim_t
+    py = (pts[:, :, :, 1] * (2 * math.pi))[:, :, :, None] / dim_t
+    px = torch.stack((px[:, :, :, 0::2].sin(), px[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    py = torch.stack((py[:, :, :, 0::2].sin(), py[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    want = torch.cat((px, py), dim=-1)
+    assert got.shape == want.shape and torch.equal(got, want)
+    assert torch.equal(decoder_glue.point_pos_embed(ref, None, d_model, temp),
+                       decoder_glue.point_pos_embed(ref, torch.ones_like(vr), d_model, temp))
+
+    tmp = torch.randn(bs, nq, npts, 2, generator=g, device="cuda") * 3
+    refn = ref.clone()
+    refn.view(-1)[7] = float("nan")
+    x = refn.clamp(min=0, max=1)
+    want = (tmp + torch.log(x.clamp(min=1e-5) / (1 - x).clamp(min=1e-5))).sigmoid()
+    got = decoder_glue.refine_points(tmp, refn)
+    assert torch.equal(torch.isnan(got), torch.isnan(want)) and bool(torch.isnan(got).view(-1)[7])
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
+    with pytest.raises(RuntimeError):
+        decoder_glue.refine_points(tmp.cpu(), refn.cpu())                        # no CPU path

@@ -10,7 +10,7 @@ from gomatching_b200.video.tracking import ClipTracker
 
 eager = "--eager" in sys.argv
 cfg = C.L.build_cfg(device="cuda")
-model = C.L.build_gomatching(cfg, seed=0, b200="transformer")
+model = C.L.build_gomatching(cfg, seed=0, b200=os.environ.get("CLIP_LEVEL", "heads"))
 frames = [torch.from_numpy(f).cuda() for f in C.L.synthetic_clip(6, 720, 1280, seed=1)]
 C.L.calibrate_detections(model, C.L.frames_to_inputs(C.L.synthetic_clip(1, 720, 1280, seed=1))[0], 40)
 ct = ClipTracker(model, overlap=False, graph=not eager)
