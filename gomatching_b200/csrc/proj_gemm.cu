@@ -95,6 +95,7 @@ struct GemmParams {
   int tmem_cols;                 // power of two >= the accumulator columns of one CTA
   int diag;                      // -DMSDA_DIAG builds only: 1 = epilogue skips its work, 2 = splitter skips the split, 4 = no MMAs,
                                  // 16 = epilogue converts but does not store
+  int split_groups;              // persistent kernel: 1 or 2 groups of four splitter warps
   int stages;                    // persistent kernel: pipeline depth (the tile-per-CTA kernels fix it at compile time)
   long long* trace;              // optional [grid][8] clock64 stamps (MSDA_GEMM_TRACE), else nullptr
 };
@@ -305,13 +306,17 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 //   * barrier init, TMEM allocation, tensor-map fetch and the bias load happen once per CTA; the TMA producer runs ahead
 //     across tile boundaries, so the pipeline never drains between tiles;
 //   * tiles are half the size (128 x BN), so the last round wastes half as much.
-//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 splitter | warps 6-9 epilogue (TMEM lane quadrant = warp & 3)
-constexpr int kPThreads = 320;
+//   * when everything fits one round (tiles <= SMs: the decoder's 2 500-token GEMMs) a CTA's life is one serial
+//     TMA -> split -> MMA chain of K blocks and the splitter's ~700 clk per block is what it waits for; a second group
+//     of four splitter warps then takes every other block (no gain, slightly worse, when CTAs run many tiles).
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2 .. 2+4G-1 splitter (G = 1 or 2 groups) | next 4 warps epilogue
+//   (TMEM lane quadrant = warp & 3)
+constexpr int kPMaxThreads = 448;
 constexpr int kPMaxStages = 6;
 constexpr int kPSlabs = 2;                   // 4 KB staging slabs per epilogue warp
 constexpr int kPBatch = 1;                   // chunks converted per proxy fence / store batch
 
-__global__ void __launch_bounds__(kPThreads, 1)
+__global__ void __launch_bounds__(kPMaxThreads, 1)
 proj_gemm_3xtf32_persistent_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                                    const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -439,13 +444,18 @@ proj_gemm_3xtf32_persistent_kernel(const __grid_constant__ CUtensorMap tm_x, con
       }
       if (trace) { trace[1] = 0; trace[2] = w_split; trace[3] = w_acc; trace[4] = clock64(); }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + 4 * p.split_groups) {
     // ===================== splitter =====================
-    const int t4 = tid - 64;                         // 0..127
-    int s = 0;
+    const int t4 = (tid - 64) & 127;                 // 0..127 within the group
+    const int grp = (warp - 2) >> 2, ngrp = p.split_groups;   // group g takes the K blocks with running index % G == g
+    int s = 0, jb = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb, ++jb) {
+        if (ngrp == 2 && (jb & 1) != grp) {
+          if (++s == stages) { s = 0; ph ^= 1u; }
+          continue;
+        }
         mbar_wait(bar_full(s), ph);
         const uint32_t xa = stage_x(s) + (uint32_t)t4 * 16u, la = stage_xl(s) + (uint32_t)t4 * 16u;
 #pragma unroll
@@ -466,7 +476,7 @@ proj_gemm_3xtf32_persistent_kernel(const __grid_constant__ CUtensorMap tm_x, con
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
-    const uint32_t slab0 = slab_base + (uint32_t)(warp - 6) * (uint32_t)(kPSlabs * 4096);
+    const uint32_t slab0 = slab_base + (uint32_t)(warp - 2 - 4 * p.split_groups) * (uint32_t)(kPSlabs * 4096);
     const int chunks = BN / 32;
     int it = 0, i = 0;
     long long w_ready = 0, busy = 0;
@@ -533,7 +543,7 @@ proj_gemm_3xtf32_persistent_kernel(const __grid_constant__ CUtensorMap tm_x, con
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
-    if (trace && tid == 192) { trace[5] = clock64(); trace[6] = w_ready; trace[7] = busy; }
+    if (trace && (warp & 3) == 2 && lane == 0) { trace[5] = clock64(); trace[6] = w_ready; trace[7] = busy; }
   }
 
   tc_fence_before();
@@ -648,13 +658,15 @@ static int linear_impl(const float* x, int ldx, const float* w_hi, const float* 
     p.trace = g_trace;
     p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K;
     p.block_n = BN; p.tmem_cols = tmem_cols; p.relu = relu; p.stages = stages;
+    p.split_groups = row_tiles * (N / BN) <= sms ? 2 : 1;
+    { const char* g = getenv("MSDA_GEMM_SPLIT_GROUPS"); if (g && (atoi(g) == 1 || atoi(g) == 2)) p.split_groups = atoi(g); }
     { const char* d = getenv("MSDA_GEMM_DIAG"); p.diag = d ? atoi(d) : 0; }
     static msda::PerDeviceOnce configured_p;
     if (configured_p.need())
       cudaFuncSetAttribute(proj_gemm_3xtf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     const long long tiles = row_tiles * (N / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    proj_gemm_3xtf32_persistent_kernel<<<grid, kPThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_y, p);
+    proj_gemm_3xtf32_persistent_kernel<<<grid, 64 + 128 * p.split_groups + 128, smem, (cudaStream_t)stream>>>(tm_x, tm_y, p);
     return (int)cudaGetLastError();
   }
 
@@ -686,7 +698,7 @@ static int linear_impl(const float* x, int ldx, const float* w_hi, const float* 
 
   GemmParams p;
   p.trace = g_trace;
-  p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K; p.block_n = BN; p.tmem_cols = tmem_cols; p.relu = relu; p.stages = 0; p.diag = 0;
+  p.w_hi = w_hi; p.w_lo = w_lo; p.y = y; p.ldy = ldy; p.bias = bias; p.row_zero = row_zero; p.M = M; p.N = N; p.K = K; p.block_n = BN; p.tmem_cols = tmem_cols; p.relu = relu; p.stages = 0; p.diag = 0; p.split_groups = 1;
   const int stages = two ? 3 : 2;
   const size_t stage_bytes = 2 * (size_t)kSubBytes * (two ? 2 : 1) + 2 * (size_t)BN * kBlockK * 4;
   size_t smem = stages * stage_bytes;

@@ -13,7 +13,7 @@ a = ap.parse_args()
 
 
 def timed(M, N, K, relu, env):
-    for k in ("MSDA_GEMM_PERSISTENT", "MSDA_GEMM_BN"):
+    for k in ("MSDA_GEMM_PERSISTENT", "MSDA_GEMM_BN", "MSDA_GEMM_SPLIT_GROUPS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     x = [torch.randn(M, K, device="cuda") for _ in range(4)]
@@ -48,6 +48,9 @@ for M in a.rows:
         res.append(("tile-per-CTA", us, err))
         us, err = timed(M, N, K, relu, {})
         res.append(("auto", us, err))
+        for g in (1, 2):
+            us, err = timed(M, N, K, relu, {"MSDA_GEMM_SPLIT_GROUPS": str(g)})
+            res.append(("auto, %d splitter group(s)" % g, us, err))
         for bn in (32, 64, 96, 128, 192, 256):
             if N % bn:
                 continue
@@ -56,4 +59,4 @@ for M in a.rows:
         tensor_us = 3 * 2.0 * M * N * K / 1.1e15 * 1e6
         print("M=%6d N=%4d K=%4d relu=%d (3 TF32 passes at 1.1 PF/s: %.1f us):" % (M, N, K, relu, tensor_us), flush=True)
         for name, us, err in res:
-            print("    %-14s %7.1f us   max err %.2e" % (name, us, err), flush=True)
+            print("    %-28s %7.1f us   max err %.2e" % (name, us, err), flush=True)
