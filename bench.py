@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--config", default="GoMatching_ICDAR15",
                     help="clip: the reference config file (configs/<name>.yaml), e.g. GoMatching_PP_DSText (BASELINE.json configs[4])")
+    ap.add_argument("--verbatim-tracker", action="store_true",
+                    help="clip: run GoMatching.run_short_term_match / run_long_term_match verbatim instead of "
+                         "video/association.py (identical IDs; the A/B for the tracker term)")
     ap.add_argument("--level", default="heads", choices=["op", "module", "layers", "transformer", "heads"],
                     help="install_into_adet level (clip)")
     ap.add_argument("--no-graph", action="store_true", help="clip: eager spotter instead of the CUDA-graph replay")
@@ -594,7 +597,8 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
         per_round = sum(weights)
         mine = [(t, s) for t, r, s in round_plan(per_round, weights)[0] if r == rank]
         cts = [ClipTracker(model, weights=weights, tracker_rank=c, overlap=True, associate=associate,
-                           host_results=host_results, graph=False if args.no_graph else graph) for c in range(clips)]
+                           host_results=host_results, graph=False if args.no_graph else graph,
+                           fast_association=not args.verbatim_tracker) for c in range(clips)]
         my = cts[rank] if rank < clips else None           # the clip this rank tracks
         sg = cts[0].spotter_graph
         k = [0]
@@ -806,6 +810,9 @@ def main():
             "parallelism": "dp%d: %d concurrent clip(s), clip c tracked on rank c; every clip's frames sharded over all ranks "
                            "(N=1 per forward), one NCCL gather of each round's records to the clip's tracker rank, the "
                            "reference's tracker in a worker thread there" % (world, clip["clips"]),
+            "tracker": ("GoMatching.run_short_term_match / run_long_term_match verbatim" if args.verbatim_tracker else
+                        "video/association.py: the reference's association modules and Hungarian step, ID bookkeeping on "
+                        "the host (track ids bit-identical to the verbatim matchers)"),
             "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "detections_per_frame": clip["detections_per_frame"],
             "score_threshold": clip["score_threshold"], "cuda_graph": clip["graph"], "spotting_only": clip["spotting_only"],
             "clocks": clocks, "e2e": clip.get("e2e"), "gpu_launches": clip["launches"],
