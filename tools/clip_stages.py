@@ -9,7 +9,8 @@ from gomatching_b200.video.tracking import ClipTracker
 
 ap = argparse.ArgumentParser(); ap.add_argument("--frames", type=int, default=24); a = ap.parse_args()
 cfg = C.L.build_cfg(device="cuda")
-model = C.L.build_gomatching(cfg, seed=0, b200="transformer")
+model = C.L.build_gomatching(cfg, seed=0, b200="heads")
+C.L.calibrate_detections(model, C.L.frames_to_inputs(C.L.synthetic_clip(1, 720, 1280, seed=1))[0], 40)
 frames = [torch.from_numpy(f).cuda() for f in C.L.synthetic_clip(a.frames, 720, 1280, seed=1)]
 ct = ClipTracker(model, overlap=False, graph=True)
 ct.feed(frames[:4])                                   # capture + warm
