@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "libmsda_b200.so")
 _lock = threading.Lock()
 _lib = None
-ABI_VERSION = 3      # include/msda_b200.h MSDA_B200_ABI_VERSION; bumped whenever the exported symbol list changes
+ABI_VERSION = 4      # include/msda_b200.h MSDA_B200_ABI_VERSION; bumped whenever the exported symbol list changes
 
 # every symbol include/msda_b200.h declares; tests/test_abi.py checks header <-> list <-> .so agree
 SYMBOLS = (
@@ -49,6 +49,8 @@ SYMBOLS = (
     "msda_b200_point_pos_embed_f32",
     "msda_b200_refine_points_f32",
     "msda_b200_resample_u8_hwc",
+    "msda_b200_jpeg_info",
+    "msda_b200_jpeg_decode_u8",
 )
 
 
@@ -150,6 +152,10 @@ def lib() -> ctypes.CDLL:
         L.msda_b200_point_pos_embed_f32.argtypes = [vp, vp, ci, vp, ctypes.c_longlong, ci, ci, vp, vp]
         L.msda_b200_refine_points_f32.restype = ci
         L.msda_b200_refine_points_f32.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp, vp]
+        L.msda_b200_jpeg_info.restype = ci
+        L.msda_b200_jpeg_info.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.msda_b200_jpeg_decode_u8.restype = ci
+        L.msda_b200_jpeg_decode_u8.argtypes = [vp, ctypes.c_size_t, ci, vp, ci, ci, vp]
         L.msda_b200_resample_u8_hwc.restype = ci
         L.msda_b200_resample_u8_hwc.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp]
         L.msda_b200_shape_mismatch_epoch.restype = ci

@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmsda_b200.so")
-SOURCES = ["msda_forward.cu", "msda_forward_fast.cu", "msda_forward_staged.cu", "msda_forward_pipelined.cu", "msda_forward_paired.cu", "msda_backward.cu", "msda_api.cu", "proj_gemm.cu", "frame_batcher.cu", "add_layernorm.cu", "small_attention.cu", "decoder_glue.cu", "frame_resize.cu"]
-HEADERS = ["msda_device.cuh", "msda_fast_common.cuh", "tma_common.cuh", "msda_launch.h", os.path.join("..", "..", "include", "msda_b200.h")]
+SOURCES = ["msda_forward.cu", "msda_forward_fast.cu", "msda_forward_staged.cu", "msda_forward_pipelined.cu", "msda_forward_paired.cu", "msda_backward.cu", "msda_api.cu", "proj_gemm.cu", "frame_batcher.cu", "add_layernorm.cu", "small_attention.cu", "decoder_glue.cu", "frame_resize.cu", "jpeg_decode.cu"]
+HEADERS = ["msda_device.cuh", "msda_fast_common.cuh", "tma_common.cuh", "msda_launch.h", "jpeg_entropy.h", os.path.join("..", "..", "include", "msda_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -31,6 +31,7 @@ import torch
 import torch.distributed as dist
 
 from .association import FastAssociation
+from .jpeg import decode_jpeg
 from .pipeline import _world, reference_association_step
 from .records import RecordSchema
 
@@ -201,7 +202,10 @@ class ClipTracker:
         """One frame as the predictor hands it to the model.  With the batcher: the uint8 HWC frame itself (BGR, as
         read); otherwise the reference's host conversion (optional RGB flip, float32 CHW)."""
         if self.use_batcher:
-            t = frame if isinstance(frame, torch.Tensor) else torch.from_numpy(frame)
+            if isinstance(frame, (bytes, bytearray, memoryview)):     # a JPEG file as read from disk: decoded on the device
+                t = decode_jpeg(frame, self.device, bgr=True)
+            else:
+                t = frame if isinstance(frame, torch.Tensor) else torch.from_numpy(frame)
             h, w = t.shape[:2]
             if self.original_size is None:
                 self.original_size = (int(h), int(w))
@@ -241,8 +245,8 @@ class ClipTracker:
     # ------------------------------------------------------------------------------------------ driver
     @torch.no_grad()
     def feed(self, frames: Sequence) -> None:
-        """Spot and associate ``frames`` (numpy / torch uint8 HWC BGR as decoded, or -- without the batcher -- the
-        reference's input dicts).  Every rank passes the same list; a rank only touches the frames it owns."""
+        """Spot and associate ``frames`` (numpy / torch uint8 HWC BGR as decoded, JPEG files as ``bytes`` -- decoded on the
+        device, video/jpeg.py -- or, without the batcher, the reference's input dicts).  Every rank passes the same list; a rank only touches the frames it owns."""
         base = self.n_fed
         for rnd in round_plan(len(frames), self.weights):
             t0 = time.perf_counter()

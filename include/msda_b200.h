@@ -41,13 +41,14 @@
 #ifndef MSDA_B200_H_
 #define MSDA_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 3
+#define MSDA_B200_ABI_VERSION 4
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define MSDA_E_NULLPTR   (-1)   /* a required pointer is NULL                                   */
@@ -271,6 +272,19 @@ int  msda_b200_forward_f32_host(msda_b200_host_ctx_t* ctx,
  * out: device float32 (N, 3, Hp, Wp).  Bit-identical to the eager ops (IEEE subtract, then IEEE divide). */
 int msda_b200_frames_u8_to_chw_f32(const unsigned char* frames, int N, int H, int W, int flip_channels,
                                    const float* mean3, const float* std3, int Hp, int Wp, float* out, void* stream);
+
+/* ---- JPEG frame decode, bit-identical to Pillow / libjpeg-turbo with default settings --------------------------------
+ * Replaces `read_image(path, format="BGR")` of the reference's video loop (eval.py:324-327: detectron2 -> PIL.Image.open
+ * -> convert("RGB") -> numpy -> BGR).  The Huffman stage runs on the calling host thread; dequantisation, the 13-bit
+ * integer inverse DCT (IJG jidctint.c), fancy chroma upsampling (jdsample.c) and the fixed-point YCbCr -> RGB conversion
+ * (jdcolor.c) run on `stream`.  Baseline / extended-sequential Huffman JPEG, 8-bit, grey or 3 components, 4:4:4 / 4:2:2 /
+ * 4:2:0, restart intervals; anything else returns MSDA_E_UNSUPPORTED (no fallback).
+ * jpeg_info: frame size from the SOF marker (host only).  jpeg_decode: data / len = the file in HOST memory; out = DEVICE
+ * uint8 (height, width, 3) contiguous, channels B,G,R if bgr else R,G,B; width / height must equal jpeg_info's.
+ * Truncated or corrupt streams return MSDA_E_DIMS.  Scratch memory comes from the stream-ordered allocator. */
+int msda_b200_jpeg_info(const unsigned char* data, size_t len, int* width, int* height, int* components);
+int msda_b200_jpeg_decode_u8(const unsigned char* data, size_t len, int bgr, unsigned char* out, int width, int height,
+                             void* stream);
 
 /* ---- test-time frame resize, bit-identical to Pillow's 8-bit bilinear resample ---------------------------------------
  * Replaces `self.aug.get_transform(x).apply_image(x)` (ResizeShortestEdge -> PIL.Image.resize(BILINEAR)) of the

@@ -32,7 +32,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_abi_version_and_error_strings():
     from gomatching_b200 import _native
     L = _native.lib()
-    assert L.msda_b200_abi_version() == _native.ABI_VERSION == 3
+    assert L.msda_b200_abi_version() == _native.ABI_VERSION == 4
     assert L.msda_b200_variant_count() >= 1
     assert b"NULL" in L.msda_b200_error_string(-1)
     assert b"2 or 4" in L.msda_b200_error_string(-4)
