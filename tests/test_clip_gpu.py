@@ -194,3 +194,27 @@ def test_device_resize_matches_the_reference_predictor_path():
         ct.close()
     C.assert_identical(runs[0], runs[1], "device resize (eager) vs host PIL resize")
     C.assert_identical(runs[0], runs[2], "device resize (graph) vs host PIL resize")
+
+
+def test_jpeg_files_as_clip_input_give_the_results_of_the_reference_frame_read():
+    """``ClipTracker.feed`` takes JPEG files as bytes and decodes them on the device (video/jpeg.py): the clip must come out
+    exactly as when every frame is read the reference's way -- Pillow on the host (read_image, eval.py:327), BGR array."""
+    import io
+    from PIL import Image
+    cfg = C.L.build_cfg(device="cuda")
+    model = C.L.build_gomatching(cfg, seed=0, b200="transformer")
+    frames = C.L.synthetic_clip(6, H, W, seed=5)
+    files, arrays = [], []
+    for f in frames:                                               # f: BGR uint8 HWC as read_image returns it
+        buf = io.BytesIO()
+        Image.fromarray(np.ascontiguousarray(f[:, :, ::-1])).save(buf, "JPEG", quality=90)
+        files.append(buf.getvalue())
+        arrays.append(np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(files[-1])).convert("RGB"))[:, :, ::-1]))
+    runs = []
+    for inputs in (arrays, files):
+        ct = ClipTracker(model, overlap=False)
+        ct.feed(inputs)
+        runs.append((C.summarize(ct.finish()), ct.id_count))
+        ct.close()
+    C.assert_identical(runs[0][0], runs[1][0], "JPEG bytes vs host-decoded arrays")
+    assert runs[0][1] == runs[1][1]
