@@ -211,6 +211,7 @@ inline int entropy_decode(const uint8_t* data, size_t len, Decoded& out) {
       out.ncomp = seg[5];
       if (out.ncomp != 1 && out.ncomp != 3) return kUnsupported;
       if (out.width <= 0 || out.height <= 0 || n < 6 + 3 * out.ncomp) return kCorrupt;
+      if ((long long)out.width * out.height > (1LL << 28)) return kUnsupported;        // 268 Mpixel: refuse absurd headers
       out.max_h = out.max_v = 1;
       for (int c = 0; c < out.ncomp; ++c) {
         Component& cp = out.comp[c];

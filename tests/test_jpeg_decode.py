@@ -137,3 +137,35 @@ def test_read_image_bgr_matches_the_reference_frame_read(tmp_path):
         want = np.asarray(ImageOps.exif_transpose(Image.open(path)).convert("RGB"))[:, :, ::-1]
         got = jpeg.read_image_bgr(path, "cuda").cpu().numpy()
         assert got.shape == want.shape and np.array_equal(got, want), orientation
+
+
+def test_entropy_decoder_survives_corrupted_streams():
+    """The host Huffman stage is shared by the oracle and the product: byte flips, stray 0xFF, deletions and insertions
+    must end in a decoded image or an error code, never in a crash or an out-of-bounds block index."""
+    from oracle import jpeg_oracle as J
+    rng = np.random.default_rng(5)
+    img = _image(67, 93, 11)
+    base = [_jpeg(img, quality=80), _jpeg(img, quality=50, subsampling=0, optimize=True),
+            _jpeg(img, quality=90, restart_marker_blocks=4), _jpeg(img, quality=70, subsampling=1)]
+    outcomes = {"ok": 0}
+    for it in range(2000):
+        d = bytearray(base[it % len(base)])
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(2, len(d)))
+            mode = int(rng.integers(0, 4))
+            if mode == 0:
+                d[pos] = int(rng.integers(0, 256))
+            elif mode == 1:
+                d[pos] = 0xFF
+            elif mode == 2:
+                del d[pos:pos + int(rng.integers(1, 20))]
+            else:
+                d[pos:pos] = bytes(rng.integers(0, 256, int(rng.integers(1, 8))).astype(np.uint8))
+        try:
+            out = J.decode_rgb(bytes(d))
+            assert out.ndim == 3 and out.shape[2] == 3
+            outcomes["ok"] += 1
+        except ValueError as e:
+            assert e.args[0] in (1, 2, 3)
+            outcomes[e.args[0]] = outcomes.get(e.args[0], 0) + 1
+    assert outcomes["ok"] > 0 and outcomes.get(2, 0) > 0 and outcomes.get(1, 0) > 0
