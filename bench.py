@@ -500,8 +500,56 @@ def run_op_workload(args, world, rank, device, steps, warmup, barrier, with_e2e)
         sub["decoder_f32_1080p_F4_300q"] = line(time_launches(lambda w: launch(w), bigd, 3), 4, bigd[0]["S"], bigd[0]["Lq"])
         del big, bigd
         torch.cuda.empty_cache()
+        sub["gemm_3xtf32"] = gemm_sublines(device)
         res["sublines"] = sub
     return res
+
+
+def gemm_sublines(device):
+    """The projection GEMM (csrc/proj_gemm.cu) at the five encoder-layer shapes of ONE 1280x720 frame (M = 19 160 tokens) and
+    at 8 frames: CUDA-event time of 20 back-to-back calls replayed from a CUDA graph (4 rotating input / output sets),
+    against the tensor-pipe bound of its three TF32 passes -- peak TF32 = half the measured dense bf16 rate."""
+    import torch
+    from gomatching_b200.projections import linear_3xtf32
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf32_peak = float(peaks.get("bf16_tflops", 2250.0)) / 2.0
+    out = {"tensor_peak_tflops_tf32": tf32_peak,
+           "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2" if "bf16_tflops" in peaks else "nominal 2250 / 2"}
+    for M_rows in (19160, 153280):
+        for name, N, K, relu in (("value_proj", 256, 256, False), ("offsets_attn", 384, 256, False), ("ffn1", 1024, 256, True),
+                                 ("ffn2", 256, 1024, False)):
+            x = [torch.randn(M_rows, K, device=device) for _ in range(4)]
+            w = torch.randn(N, K, device=device) * 0.05
+            b = torch.randn(N, device=device)
+            y = [torch.empty(M_rows, N, device=device) for _ in range(4)]
+            linear_3xtf32(x[0], w, b, out=y[0], relu=relu)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(gr, stream=st):
+                    for i in range(20):
+                        linear_3xtf32(x[i % 4], w, b, out=y[i % 4], relu=relu)
+            gr.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 40 * 1e3
+            mma_tflops = 3 * 2.0 * M_rows * N * K / us / 1e6
+            out["%s_M%d" % (name, M_rows)] = {"N": N, "K": K, "us_per_call": us, "tf32_mma_tflops": mma_tflops,
+                                              "frac_of_tensor_peak": mma_tflops / tf32_peak,
+                                              "GBps": (M_rows * K + M_rows * N + 2 * N * K) * 4 / us / 1e3}
+            del x, y, gr
+            torch.cuda.empty_cache()
+    return out
 
 
 def reference_loop_on_gpu(args, device, frames=16):
@@ -665,6 +713,20 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
                       "d2h_bytes_per_step": int(info_e["d2h"]), "ms_per_step": ms_e, "steps": steps,
                       "api": "gomatching_b200.video.ClipTracker.feed(pinned uint8 HWC frames) -> per-frame track ids on the "
                              "host (frame H2D, frame-batcher kernel, spotter, record gather, reference tracker, ids D2H)"}
+    if not args.no_e2e and world == 1 and not args.no_sublines:
+        # the same end-to-end loop fed with the frames as JPEG FILES (quality 90, 4:2:0): host Huffman stage in the
+        # ClipTracker's decode-ahead threads, IDCT / upsampling / colour conversion on the device (bit-identical to Pillow)
+        import io
+        from PIL import Image
+        jpeg_pool = []
+        for f in clip:
+            buf = io.BytesIO()
+            Image.fromarray(f[:, :, ::-1].copy()).save(buf, "JPEG", quality=90)
+            jpeg_pool.append(buf.getvalue())
+        ms_j, info_j, _ = run(jpeg_pool, steps, clips=1, host_results=True)
+        res["e2e_jpeg"] = {"value": info_j["per_step"] / (ms_j * 1e-3), "unit": "frames/s", "ms_per_step": ms_j,
+                           "jpeg_bytes_per_frame": int(sum(len(b) for b in jpeg_pool) / len(jpeg_pool)),
+                           "api": "ClipTracker.feed(JPEG files as bytes) -> per-frame track ids on the host"}
     if clips > 1:
         # ONE clip over all N GPUs (BASELINE.json configs[3] read literally): one tracker for the whole job -- the Amdahl term
         ms_1, info_1, _ = run(dev_pool, max(3, steps // 2), clips=1)
@@ -815,7 +877,7 @@ def main():
                         "the host (track ids bit-identical to the verbatim matchers)"),
             "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "detections_per_frame": clip["detections_per_frame"],
             "score_threshold": clip["score_threshold"], "cuda_graph": clip["graph"], "spotting_only": clip["spotting_only"],
-            "clocks": clocks, "e2e": clip.get("e2e"), "gpu_launches": clip["launches"],
+            "clocks": clocks, "e2e": clip.get("e2e"), "e2e_jpeg": clip.get("e2e_jpeg"), "gpu_launches": clip["launches"],
             "gpu_launches_note": "kernel-launching C-ABI calls of libmsda_b200.so in the timed region, all ranks (each "
                                  "enqueues >= 1 kernel); cuDNN / cuBLAS kernels of the reference's eager code not counted",
             "roofline": roofline, "cpu_baseline": cpu, "reference_on_gpu": ref_gpu, "msda": msda, "msda_hbm_gbs": achieved,

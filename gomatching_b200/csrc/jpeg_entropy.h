@@ -50,12 +50,17 @@ static const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 
                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+constexpr int kLook = 12;                 // bits of lookahead in the symbol and fast-AC tables
+
+inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+
 struct HuffTable {
   bool set = false;
   uint8_t bits[17];
   uint8_t vals[256];
   int mincode[17], maxcode[18], valptr[17];
-  uint8_t look_len[256], look_val[256];   // 8-bit lookahead
+  uint8_t look_len[1 << kLook], look_val[1 << kLook];   // symbol of every kLook-bit prefix that holds a whole code
+  int32_t fast_ac[1 << kLook];   // AC tables: (value << 8) | (run << 4) | (code + magnitude bits) when both fit the prefix
   int build() {
     int code = 0, k = 0;
     for (int l = 1; l <= 16; ++l) {
@@ -70,14 +75,20 @@ struct HuffTable {
     maxcode[17] = 0x7fffffff;
     if (k > 256) return kCorrupt;
     memset(look_len, 0, sizeof(look_len));
+    memset(fast_ac, 0, sizeof(fast_ac));
     int c = 0;
     k = 0;
-    for (int l = 1; l <= 8; ++l) {
+    for (int l = 1; l <= kLook; ++l) {
       for (int i = 0; i < bits[l]; ++i, ++k, ++c) {
-        const int first = c << (8 - l);
-        for (int j = 0; j < (1 << (8 - l)); ++j) {
+        const int first = c << (kLook - l);
+        for (int j = 0; j < (1 << (kLook - l)); ++j) {
           look_len[first + j] = (uint8_t)l;
           look_val[first + j] = vals[k];
+          const int run = vals[k] >> 4, mag = vals[k] & 15;
+          if (mag && l + mag <= kLook) {
+            const int v = extend(((first + j) >> (kLook - l - mag)) & ((1 << mag) - 1), mag);
+            fast_ac[first + j] = (v * 256) + (run * 16) + (l + mag);
+          }
         }
       }
       c <<= 1;
@@ -89,13 +100,26 @@ struct HuffTable {
 struct BitReader {
   const uint8_t* p;
   const uint8_t* end;
-  uint32_t acc = 0;
+  uint64_t acc = 0;
   int nbits = 0;
   bool hit_marker = false;      // a marker was met: the stream is padded with zero bits from here on
   bool eof = false;             // ... or the data ended without one
-  void fill() {
-    while (nbits <= 24) {
-      int byte = 0;
+  void fill() {                 // tops the accumulator up to more than 56 bits
+    if (!hit_marker && end - p >= 8 && nbits <= 32) {
+      uint64_t v;
+      memcpy(&v, p, 8);
+      v = __builtin_bswap64(v);
+      const uint64_t inv = ~v;                                                  // a zero byte of inv = an 0xFF byte of v
+      if (!((inv - 0x0101010101010101ull) & ~inv & 0x8080808080808080ull)) {    // no marker / stuffing in the next 8 bytes
+        const int take = (64 - nbits) >> 3;                                     // whole bytes that fit
+        acc |= (v >> (64 - 8 * take)) << (64 - nbits - 8 * take);
+        p += take;
+        nbits += 8 * take;
+        return;
+      }
+    }
+    while (nbits <= 56) {
+      uint64_t byte = 0;
       if (!hit_marker && p < end) {
         byte = *p;
         if (byte == 0xff) {
@@ -112,15 +136,14 @@ struct BitReader {
         if (!hit_marker) eof = true;
         hit_marker = true;
       }
-      acc |= (uint32_t)byte << (24 - nbits);
+      acc |= byte << (56 - nbits);
       nbits += 8;
     }
   }
-  int peek(int n) { return (int)(acc >> (32 - n)); }
+  int peek(int n) { return (int)(acc >> (64 - n)); }
   void skip(int n) { acc <<= n; nbits -= n; }
-  int get(int n) {
+  int get(int n) {              // n <= 16; the caller keeps nbits >= 32
     if (n == 0) return 0;
-    if (nbits < n) fill();
     const int v = peek(n);
     skip(n);
     return v;
@@ -128,16 +151,16 @@ struct BitReader {
   void reset() { acc = 0; nbits = 0; hit_marker = false; }
 };
 
+// needs nbits >= 16
 inline int decode_symbol(BitReader& br, const HuffTable& t) {
-  if (br.nbits < 16) br.fill();
-  const int look = br.peek(8);
+  const int look = br.peek(kLook);
   int l = t.look_len[look];
   if (l) {
     br.skip(l);
     return t.look_val[look];
   }
-  int code = br.peek(9);
-  l = 9;
+  l = kLook + 1;
+  int code = br.peek(l);
   while (l <= 16 && code > t.maxcode[l]) {
     ++l;
     if (l > 16) break;
@@ -150,9 +173,8 @@ inline int decode_symbol(BitReader& br, const HuffTable& t) {
   return t.vals[idx];
 }
 
-inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
-
 inline int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac, int& pred, int16_t* out) {
+  if (br.nbits < 32) br.fill();
   int s = decode_symbol(br, dc);
   if (s < 0 || s > 16) return kCorrupt;
   int diff = 0;
@@ -160,6 +182,15 @@ inline int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac,
   pred += diff;
   out[0] = (int16_t)pred;
   for (int k = 1; k < 64;) {
+    if (br.nbits < 32) br.fill();
+    const int f = ac.fast_ac[br.peek(kLook)];
+    if (f) {                     // run, size and the magnitude bits all inside the lookahead
+      k += (f >> 4) & 15;
+      if (k > 63) return kCorrupt;
+      br.skip(f & 15);
+      out[kZigzag[k++]] = (int16_t)(f >> 8);
+      continue;
+    }
     const int rs = decode_symbol(br, ac);
     if (rs < 0) return kCorrupt;
     const int r = rs >> 4, sz = rs & 15;
@@ -184,7 +215,9 @@ inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
 inline int entropy_decode(const uint8_t* data, size_t len, Decoded& out) {
   using namespace detail;
   if (len < 4 || data[0] != 0xff || data[1] != 0xd8) return kCorrupt;
-  HuffTable dc_tab[4], ac_tab[4];
+  std::vector<HuffTable> tables(8);      // 4 DC + 4 AC; ~20 KB each with the lookahead tables: not on the stack
+  HuffTable* dc_tab = tables.data();
+  HuffTable* ac_tab = tables.data() + 4;
   int restart_interval = 0;
   bool saw_sof = false, saw_jfif = false, saw_adobe = false;
   int adobe_transform = 0;

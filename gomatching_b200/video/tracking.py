@@ -53,6 +53,43 @@ def round_plan(n_frames: int, weights: Sequence[int]) -> List[List[Tuple[int, in
     return rounds
 
 
+class _JpegPrefetch:
+    """Decode-ahead for JPEG inputs: the Huffman stage of ``decode_jpeg`` is host work (ctypes releases the GIL), so the
+    frames a rank owns are decoded by a few worker threads, each on its own CUDA stream, while the rank spots earlier
+    frames; the consumer waits on the frame's event."""
+
+    def __init__(self, device, workers: int = 4, ahead: int = 8):
+        from concurrent.futures import ThreadPoolExecutor
+        self.device = device
+        self.pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="jpeg-decode")
+        self.local = threading.local()
+        self.ahead = ahead
+
+    def _decode(self, data):
+        st = getattr(self.local, "stream", None)
+        if st is None:
+            st = self.local.stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.device(self.device), torch.cuda.stream(st):
+            img = decode_jpeg(data, self.device, bgr=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        return img, ev
+
+    def submit(self, data):
+        return self.pool.submit(self._decode, data)
+
+    @staticmethod
+    def take(fut):
+        img, ev = fut.result()
+        cur = torch.cuda.current_stream(img.device)
+        cur.wait_event(ev)
+        img.record_stream(cur)
+        return img
+
+    def shutdown(self):
+        self.pool.shutdown(wait=False, cancel_futures=True)
+
+
 class _Association(threading.Thread):
     """Tracker-rank worker: consumes gathered rounds in order and runs the reference's ID assignment."""
 
@@ -138,6 +175,7 @@ class ClipTracker:
         self.associate = associate            # False: records are gathered and dropped (spotting-only measurement)
         self.host_results = host_results      # True: every frame's track ids are copied to the host as they are assigned
         self.host_ids: list = []
+        self._prefetch: Optional[_JpegPrefetch] = None
         self._worker: Optional[_Association] = None
         if overlap and self.rank == tracker_rank:
             self._worker = _Association(self)
@@ -204,6 +242,8 @@ class ClipTracker:
         if self.use_batcher:
             if isinstance(frame, (bytes, bytearray, memoryview)):     # a JPEG file as read from disk: decoded on the device
                 t = decode_jpeg(frame, self.device, bgr=True)
+            elif hasattr(frame, "result"):                            # ... ahead of time by the prefetch threads
+                t = _JpegPrefetch.take(frame)
             else:
                 t = frame if isinstance(frame, torch.Tensor) else torch.from_numpy(frame)
             h, w = t.shape[:2]
@@ -248,12 +288,31 @@ class ClipTracker:
         """Spot and associate ``frames`` (numpy / torch uint8 HWC BGR as decoded, JPEG files as ``bytes`` -- decoded on the
         device, video/jpeg.py -- or, without the batcher, the reference's input dicts).  Every rank passes the same list; a rank only touches the frames it owns."""
         base = self.n_fed
-        for rnd in round_plan(len(frames), self.weights):
+        plan = round_plan(len(frames), self.weights)
+        # JPEG inputs of this rank: decoded a few frames ahead by worker threads (host Huffman stage off the spotting thread)
+        mine = [t for rnd in plan for t, r, _ in rnd if r == self.rank]
+        pending = {}
+        if self.use_batcher and self.device.type == "cuda" and any(isinstance(frames[t], (bytes, bytearray, memoryview)) for t in mine):
+            if self._prefetch is None:
+                self._prefetch = _JpegPrefetch(self.device)
+            order = [t for t in mine if isinstance(frames[t], (bytes, bytearray, memoryview))]
+            nxt = [0]
+
+            def top_up():
+                while nxt[0] < len(order) and len(pending) < self._prefetch.ahead:
+                    pending[order[nxt[0]]] = self._prefetch.submit(frames[order[nxt[0]]])
+                    nxt[0] += 1
+            top_up()
+        for rnd in plan:
             t0 = time.perf_counter()
             block = self.schema.empty(self.max_slots, device=self.device)
             for t, r, s in rnd:
                 if r == self.rank:
-                    fields, size = self._spot(frames[t])
+                    frame = frames[t]
+                    if t in pending:
+                        frame = pending.pop(t)
+                        top_up()
+                    fields, size = self._spot(frame)
                     self.schema.pack_into(block[s], fields, base + t, size)
             self.spot_s += time.perf_counter() - t0
             gathered = self._gather(block)
@@ -301,6 +360,9 @@ class ClipTracker:
 
     def close(self) -> None:
         """Give the model back its own forwards (undo the graph / batcher patches)."""
+        if self._prefetch is not None:
+            self._prefetch.shutdown()
+            self._prefetch = None
         if self.spotter_graph is not None:
             self.spotter_graph.disable()
         self.model.__dict__.pop("preprocess_image", None)
