@@ -15,6 +15,14 @@ The data-dependent tail of ``inference`` (score threshold, NMS, the association 
 ``forward`` attributes are pointed at the replayed buffers for the duration of a call, so ``GoMatching.inference``
 itself (:268-351) still drives the frame.  The captured kernels are the ones eager execution launches, in the same
 order, so the outputs are bit-identical to the eager path (tests/test_clip_gpu.py).
+
+Replay-ahead.  The eager tail of frame t (1.7 ms of reference Python with a dozen synchronisations) used to leave the GPU
+idle before frame t + 1's replay (7.3 ms) was even enqueued.  There are therefore TWO captured buffer sets per frame size,
+used alternately, and the replays run on their own stream: when ``inference`` asks for frame t, frame t + 1 (announced by
+``ClipTracker.feed`` through ``next_frame``) is copied into the other set and replayed behind it at once, so the GPU works
+on it while the calling thread runs frame t's tail on its own stream.  A set is rewritten only after the tail has cloned
+its outputs (``free`` event); the consumer waits for the set's ``done`` event.  Same kernels, same order per frame:
+results unchanged.
 """
 from __future__ import annotations
 
@@ -61,6 +69,8 @@ class _FrameGraph:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.img, self.out, self.re = body()
         self.calls = _native.calls - calls0          # kernel-launching C-ABI calls of this library inside one replay
+        self.done: Optional[torch.cuda.Event] = None   # recorded on the replay stream after the newest replay into this set
+        self.free: Optional[torch.cuda.Event] = None   # recorded by the consumer once it has cloned this set's outputs
         # The captured launches hold raw pointers to weight-derived tensors that live OUTSIDE the graph's memory pool
         # (TF32 weight splits, merged query projections): keep them alive for as long as the graph exists.  Weights are
         # baked in at capture time -- GoMatching's spotter is frozen; after changing them call GraphedSpotter.reset().
@@ -71,6 +81,22 @@ class _FrameGraph:
     def replay(self, frame: torch.Tensor):
         self.frame.copy_(frame, non_blocking=True)
         self.graph.replay()
+
+    def launch(self, frame: torch.Tensor, stream: "torch.cuda.Stream"):
+        """Copy ``frame`` in and replay on ``stream``, after the frame exists (it was produced on the current stream) and
+        after the previous consumer of this buffer set has cloned its outputs."""
+        cur = torch.cuda.current_stream(frame.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        stream.wait_event(ready)
+        if self.free is not None:
+            stream.wait_event(self.free)
+            self.free = None
+        with torch.cuda.stream(stream):
+            self.replay(frame)
+            self.done = torch.cuda.Event()
+            self.done.record(stream)
+        frame.record_stream(stream)
 
 
 class GraphedSpotter:
@@ -85,7 +111,13 @@ class GraphedSpotter:
         self.mean, self.std = list(cfg.MODEL.PIXEL_MEAN), list(cfg.MODEL.PIXEL_STD)
         self.flip = input_format == "RGB"
         self.test_size = None                        # (MIN_SIZE_TEST, MAX_SIZE_TEST) or None: set by ClipTracker
-        self.graphs: Dict[Tuple[int, int], _FrameGraph] = {}
+        self.graphs: Dict[Tuple[int, int], list] = {}      # frame size -> [buffer set A, buffer set B]
+        self.turn: Dict[Tuple[int, int], int] = {}
+        self.replay_stream: Optional[torch.cuda.Stream] = None
+        self.next_frame: Optional[torch.Tensor] = None     # set by ClipTracker.feed: the frame inference() will ask for next
+        self.inflight = None                               # (frame tensor, buffer set) already replaying
+        self.replay_ahead = True
+        self.prefetched = 0
         self.current: Optional[_FrameGraph] = None
         self.enabled = False
         self.replays = 0
@@ -100,39 +132,74 @@ class GraphedSpotter:
             raise ValueError("the graphed spotter takes one uint8 (H, W, 3) frame per forward")
         f = frames[0]
         hw = (int(f.shape[0]), int(f.shape[1]))
-        g = self.graphs.get(hw)
-        if g is None:
+        sets = self.graphs.get(hw)
+        if sets is None:
             if len(self.graphs) >= 4:                # a clip has one frame size; do not hoard activations of old ones
-                self.graphs.clear()
+                self.reset()
             try:
                 with self.eager():
-                    g = _FrameGraph(self, hw)
+                    sets = [_FrameGraph(self, hw), _FrameGraph(self, hw)] if self.replay_ahead else [_FrameGraph(self, hw)]
             except Exception as e:                   # not capturable in this configuration: stay eager, say why
                 self.failed = "%s: %s" % (type(e).__name__, e)
                 self.disable()
                 torch.cuda.synchronize(self.device)
                 return self.model.preprocess_image(batched_inputs)
-            self.graphs[hw] = g
-        g.replay(f)
+            self.graphs[hw] = sets
+            self.turn[hw] = 0
+        if self.replay_stream is None:
+            self.replay_stream = torch.cuda.Stream(device=self.device)
+        if self.inflight is not None and self.inflight[0] is f:
+            g = self.inflight[1]                     # announced by the previous call: already replaying
+            self.prefetched += 1
+        else:
+            g = self._launch(f, sets, hw)
+        self.inflight = None
+        nf, self.next_frame = self.next_frame, None
+        if nf is not None and self.replay_ahead and (int(nf.shape[0]), int(nf.shape[1])) == hw and nf.dtype == torch.uint8:
+            self.inflight = (nf, self._launch(nf, sets, hw))      # the next frame goes to the GPU before this frame's tail starts
+        torch.cuda.current_stream(self.device).wait_event(g.done)
         self.replays += 1
         self.replayed_calls += g.calls
         self.current = g
         return self.ImageList(g.img, [g.size])
+
+    def _launch(self, f, sets, hw) -> _FrameGraph:
+        g = sets[self.turn[hw] % len(sets)]
+        self.turn[hw] += 1
+        g.launch(f, self.replay_stream)
+        return g
+
+    def _consumed(self):
+        """The tail holds clones of everything it needs from the current buffer set: the set may be rewritten."""
+        g = self.current
+        if g is not None:
+            g.free = torch.cuda.Event()
+            g.free.record(torch.cuda.current_stream(self.device))
 
     def _backbone(self, images):
         return None, None                            # consumed only by detection_transformer, which is replayed too
 
     def _detection_transformer(self, features, pos, backbone):
         # fresh tensors: inference() and detection() modify their inputs in place (:590-603)
-        return {k: (v.clone() if v is not None else None) for k, v in self.current.out.items()}
+        out = {k: (v.clone() if v is not None else None) for k, v in self.current.out.items()}
+        if not self.model.with_rescore:
+            self._consumed()
+        return out
 
     def _rescoring_head(self, query_features):
-        return self.current.re.clone()
+        re = self.current.re.clone()
+        self._consumed()                              # called after detection_transformer (gom_lstmatcher.py:286-288)
+        return re
 
     def reset(self):
         """Forget the captured graphs (after the model's weights changed); the next frame re-captures."""
+        if self.replay_stream is not None:
+            self.replay_stream.synchronize()
         self.graphs.clear()
+        self.turn.clear()
         self.current = None
+        self.inflight = None
+        self.next_frame = None
 
     def enable(self):
         if self.enabled:
@@ -158,6 +225,8 @@ class GraphedSpotter:
             if mod is not None:
                 mod.__dict__.pop("forward", None)
         self.enabled = False
+        self.inflight = None
+        self.next_frame = None
 
     class _Eager:
         def __init__(self, sp):

@@ -259,8 +259,8 @@ class ClipTracker:
         return {"image": torch.as_tensor(x.astype("float32").transpose(2, 0, 1)), "height": h, "width": w,
                 "video_id": 0}
 
-    def _spot(self, frame) -> Tuple[Dict[str, torch.Tensor], Tuple[int, int]]:
-        inst = self.model.inference([self._to_input(frame)], self.time_cost)[0]
+    def _spot(self, frame, prepared_input: bool = False) -> Tuple[Dict[str, torch.Tensor], Tuple[int, int]]:
+        inst = self.model.inference([frame if prepared_input else self._to_input(frame)], self.time_cost)[0]
         fields = {k: (v.tensor if isinstance(v, self._Boxes) else v) for k, v in inst.get_fields().items()}
         return fields, tuple(int(s) for s in inst.image_size)
 
@@ -292,6 +292,9 @@ class ClipTracker:
         # JPEG inputs of this rank: decoded a few frames ahead by worker threads (host Huffman stage off the spotting thread)
         mine = [t for rnd in plan for t, r, _ in rnd if r == self.rank]
         pending = {}
+
+        def top_up():
+            pass
         if self.use_batcher and self.device.type == "cuda" and any(isinstance(frames[t], (bytes, bytearray, memoryview)) for t in mine):
             if self._prefetch is None:
                 self._prefetch = _JpegPrefetch(self.device)
@@ -303,16 +306,29 @@ class ClipTracker:
                     pending[order[nxt[0]]] = self._prefetch.submit(frames[order[nxt[0]]])
                     nxt[0] += 1
             top_up()
+        # replay-ahead (video/spotter_graph.py): while frame t's eager tail runs, frame t + 1 is already on the GPU; the
+        # graphed spotter is told which tensor inference() will ask for next
+        sg = self.spotter_graph if (self.spotter_graph is not None and self.spotter_graph.enabled) else None
+        nxt_of = {a: b for a, b in zip(mine, mine[1:])}
+        prepared = {}
+
+        def fetch(t):
+            frame = frames[t]
+            if t in pending:
+                frame = pending.pop(t)
+                top_up()
+            return self._to_input(frame)
+
         for rnd in plan:
             t0 = time.perf_counter()
             block = self.schema.empty(self.max_slots, device=self.device)
             for t, r, s in rnd:
                 if r == self.rank:
-                    frame = frames[t]
-                    if t in pending:
-                        frame = pending.pop(t)
-                        top_up()
-                    fields, size = self._spot(frame)
+                    inp = prepared.pop(t) if t in prepared else fetch(t)
+                    if sg is not None and t in nxt_of and isinstance(inp, dict) and torch.is_tensor(inp.get("image")):
+                        prepared[nxt_of[t]] = fetch(nxt_of[t])
+                        sg.next_frame = prepared[nxt_of[t]]["image"]
+                    fields, size = self._spot(inp, prepared_input=True)
                     self.schema.pack_into(block[s], fields, base + t, size)
             self.spot_s += time.perf_counter() - t0
             gathered = self._gather(block)

@@ -17,7 +17,7 @@ ct = ClipTracker(model, overlap=False, graph=not eager)
 ct.feed(frames[:5])
 torch.cuda.synchronize()
 if "--graph-only" in sys.argv:                      # the replayed spotter graph alone (no eager tail, no tracker)
-    g = next(iter(ct.spotter_graph.graphs.values()))
+    g = next(iter(ct.spotter_graph.graphs.values()))[0]
     torch.cuda.cudart().cudaProfilerStart()
     g.replay(frames[5])
     torch.cuda.synchronize()

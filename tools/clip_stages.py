@@ -15,7 +15,7 @@ frames = [torch.from_numpy(f).cuda() for f in C.L.synthetic_clip(a.frames, 720, 
 ct = ClipTracker(model, overlap=False, graph=True)
 ct.feed(frames[:4])                                   # capture + warm
 sg = ct.spotter_graph
-g = next(iter(sg.graphs.values()))
+g = next(iter(sg.graphs.values()))[0]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); e0.record()
 for _ in range(10): g.graph.replay()
