@@ -17,11 +17,12 @@ itself (:268-351) still drives the frame.  The captured kernels are the ones eag
 order, so the outputs are bit-identical to the eager path (tests/test_clip_gpu.py).
 
 Replay-ahead.  The eager tail of frame t (1.7 ms of reference Python with a dozen synchronisations) used to leave the GPU
-idle before frame t + 1's replay (7.3 ms) was even enqueued.  There are therefore TWO captured buffer sets per frame size,
-used alternately, and the replays run on their own stream: when ``inference`` asks for frame t, frame t + 1 (announced by
-``ClipTracker.feed`` through ``next_frame``) is copied into the other set and replayed behind it at once, so the GPU works
-on it while the calling thread runs frame t's tail on its own stream.  A set is rewritten only after the tail has cloned
-its outputs (``free`` event); the consumer waits for the set's ``done`` event.  Same kernels, same order per frame:
+idle before frame t + 1's replay (7.3 ms) was even enqueued.  There are therefore ``depth + 1`` captured buffer sets per
+frame size, used round-robin, and the replays run on ``depth`` streams of their own: when ``inference`` asks for frame t,
+the frames ``ClipTracker.feed`` announced through ``next_frames`` (t + 1, t + 2) are copied into free sets and replayed at
+once, so the GPU works on them -- two frames overlapping, which also fills the gaps between a replay's many small
+kernels -- while the calling thread runs frame t's tail on its own stream.  A set is rewritten only after the tail has
+cloned its outputs (``free`` event); the consumer waits for the set's ``done`` event.  Same kernels, same order per frame:
 results unchanged.
 """
 from __future__ import annotations
@@ -111,11 +112,12 @@ class GraphedSpotter:
         self.mean, self.std = list(cfg.MODEL.PIXEL_MEAN), list(cfg.MODEL.PIXEL_STD)
         self.flip = input_format == "RGB"
         self.test_size = None                        # (MIN_SIZE_TEST, MAX_SIZE_TEST) or None: set by ClipTracker
-        self.graphs: Dict[Tuple[int, int], list] = {}      # frame size -> [buffer set A, buffer set B]
+        self.graphs: Dict[Tuple[int, int], list] = {}      # frame size -> depth + 1 buffer sets, used round-robin
         self.turn: Dict[Tuple[int, int], int] = {}
-        self.replay_stream: Optional[torch.cuda.Stream] = None
-        self.next_frame: Optional[torch.Tensor] = None     # set by ClipTracker.feed: the frame inference() will ask for next
-        self.inflight = None                               # (frame tensor, buffer set) already replaying
+        self.depth = 2                                     # replays in flight beyond the frame being consumed
+        self.replay_streams: list = []                     # one per frame in flight: consecutive frames overlap on the GPU
+        self.next_frames: list = []                        # set by ClipTracker.feed: the frames inference() will ask for next
+        self.inflight: list = []                           # [(frame tensor, buffer set)] already replaying, in order
         self.replay_ahead = True
         self.prefetched = 0
         self.current: Optional[_FrameGraph] = None
@@ -138,7 +140,7 @@ class GraphedSpotter:
                 self.reset()
             try:
                 with self.eager():
-                    sets = [_FrameGraph(self, hw), _FrameGraph(self, hw)] if self.replay_ahead else [_FrameGraph(self, hw)]
+                    sets = [_FrameGraph(self, hw) for _ in range(self.depth + 1 if self.replay_ahead else 1)]
             except Exception as e:                   # not capturable in this configuration: stay eager, say why
                 self.failed = "%s: %s" % (type(e).__name__, e)
                 self.disable()
@@ -146,17 +148,22 @@ class GraphedSpotter:
                 return self.model.preprocess_image(batched_inputs)
             self.graphs[hw] = sets
             self.turn[hw] = 0
-        if self.replay_stream is None:
-            self.replay_stream = torch.cuda.Stream(device=self.device)
-        if self.inflight is not None and self.inflight[0] is f:
-            g = self.inflight[1]                     # announced by the previous call: already replaying
+        if not self.replay_streams:
+            self.replay_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, self.depth))]
+        if self.inflight and self.inflight[0][0] is f:
+            g = self.inflight.pop(0)[1]              # announced by an earlier call: already replaying
             self.prefetched += 1
         else:
+            self.inflight = []                       # out of order (another clip's frame): whatever flies is dropped
             g = self._launch(f, sets, hw)
-        self.inflight = None
-        nf, self.next_frame = self.next_frame, None
-        if nf is not None and self.replay_ahead and (int(nf.shape[0]), int(nf.shape[1])) == hw and nf.dtype == torch.uint8:
-            self.inflight = (nf, self._launch(nf, sets, hw))      # the next frame goes to the GPU before this frame's tail starts
+        ahead, self.next_frames = self.next_frames, []
+        if self.replay_ahead and len(sets) > 1:
+            for nf in ahead[:self.depth]:            # the next frames go to the GPU before this frame's tail starts
+                if any(nf is x for x, _ in self.inflight):
+                    continue
+                if len(self.inflight) >= self.depth or (int(nf.shape[0]), int(nf.shape[1])) != hw or nf.dtype != torch.uint8:
+                    break
+                self.inflight.append((nf, self._launch(nf, sets, hw)))
         torch.cuda.current_stream(self.device).wait_event(g.done)
         self.replays += 1
         self.replayed_calls += g.calls
@@ -165,8 +172,8 @@ class GraphedSpotter:
 
     def _launch(self, f, sets, hw) -> _FrameGraph:
         g = sets[self.turn[hw] % len(sets)]
+        g.launch(f, self.replay_streams[self.turn[hw] % len(self.replay_streams)])
         self.turn[hw] += 1
-        g.launch(f, self.replay_stream)
         return g
 
     def _consumed(self):
@@ -193,13 +200,13 @@ class GraphedSpotter:
 
     def reset(self):
         """Forget the captured graphs (after the model's weights changed); the next frame re-captures."""
-        if self.replay_stream is not None:
-            self.replay_stream.synchronize()
+        for st in self.replay_streams:
+            st.synchronize()
         self.graphs.clear()
         self.turn.clear()
         self.current = None
-        self.inflight = None
-        self.next_frame = None
+        self.inflight = []
+        self.next_frames = []
 
     def enable(self):
         if self.enabled:
@@ -225,8 +232,8 @@ class GraphedSpotter:
             if mod is not None:
                 mod.__dict__.pop("forward", None)
         self.enabled = False
-        self.inflight = None
-        self.next_frame = None
+        self.inflight = []
+        self.next_frames = []
 
     class _Eager:
         def __init__(self, sp):

@@ -99,7 +99,8 @@ class _Association(threading.Thread):
         self.q: "queue.Queue" = queue.Queue()
         self.error: Optional[BaseException] = None
         self.busy_s = 0.0
-        self.stream = torch.cuda.Stream(device=tracker.device) if tracker.device.type == "cuda" else None
+        # high priority: the matcher's many tiny kernels must not queue behind the replays of the frames in flight
+        self.stream = torch.cuda.Stream(device=tracker.device, priority=-1) if tracker.device.type == "cuda" else None
 
     def run(self):
         try:
@@ -325,9 +326,16 @@ class ClipTracker:
             for t, r, s in rnd:
                 if r == self.rank:
                     inp = prepared.pop(t) if t in prepared else fetch(t)
-                    if sg is not None and t in nxt_of and isinstance(inp, dict) and torch.is_tensor(inp.get("image")):
-                        prepared[nxt_of[t]] = fetch(nxt_of[t])
-                        sg.next_frame = prepared[nxt_of[t]]["image"]
+                    if sg is not None and isinstance(inp, dict) and torch.is_tensor(inp.get("image")):
+                        ahead, a = [], t
+                        for _ in range(sg.depth):
+                            a = nxt_of.get(a)
+                            if a is None:
+                                break
+                            if a not in prepared:
+                                prepared[a] = fetch(a)
+                            ahead.append(prepared[a]["image"])
+                        sg.next_frames = ahead
                     fields, size = self._spot(inp, prepared_input=True)
                     self.schema.pack_into(block[s], fields, base + t, size)
             self.spot_s += time.perf_counter() - t0
