@@ -181,6 +181,12 @@ class ClipTracker:
         if overlap and self.rank == tracker_rank:
             self._worker = _Association(self)
             self._worker.start()
+            # two Python threads now share the GIL (spotting + matcher); CPython hands it over only every 5 ms by default,
+            # long enough for the replay queue of the spotting thread to run dry.  GOM_SWITCH_INTERVAL (seconds) overrides.
+            import os
+            si = float(os.environ.get("GOM_SWITCH_INTERVAL", "0.0005"))
+            if si > 0 and sys.getswitchinterval() > si:
+                sys.setswitchinterval(si)
         shared = model.__dict__.get("_msda_b200_spotter_graph")
         if shared is not None:
             shared.disable()                  # another ClipTracker of this model enabled it: re-point after the batcher below
