@@ -90,6 +90,8 @@ class _FrameGraph:
         ready = torch.cuda.Event()
         ready.record(cur)
         stream.wait_event(ready)
+        if self.done is not None:                    # the previous replay into this set may have run on the other stream (and,
+            stream.wait_event(self.done)             # if its frame was dropped, was never consumed): never two writers at once
         if self.free is not None:
             stream.wait_event(self.free)
             self.free = None
