@@ -636,7 +636,7 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
             return float(t.item())
         return x
 
-    def run(pool, n_steps, clips=1, associate=True, host_results=False, graph=None):
+    def run(pool, n_steps, clips=1, associate=True, host_results=False, graph=None, verbatim=None):
         """`clips` concurrent clips; clip c's tracker lives on rank c; every clip's round shards F frames to every rank
         (the tracker rank of a SINGLE clip spots --tracker-frames instead).  One step = one round of every clip.  Returns
         (ms per step by CUDA events incl. the association tail -- max over ranks, info, sampler event log)."""
@@ -646,7 +646,7 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
         mine = [(t, s) for t, r, s in round_plan(per_round, weights)[0] if r == rank]
         cts = [ClipTracker(model, weights=weights, tracker_rank=c, overlap=True, associate=associate,
                            host_results=host_results, graph=False if args.no_graph else graph,
-                           fast_association=not args.verbatim_tracker) for c in range(clips)]
+                           fast_association=not (args.verbatim_tracker if verbatim is None else verbatim)) for c in range(clips)]
         my = cts[rank] if rank < clips else None           # the clip this rank tracks
         sg = cts[0].spotter_graph
         k = [0]
@@ -713,6 +713,12 @@ def run_clip_workload(args, world, rank, device, steps, warmup, barrier):
                       "d2h_bytes_per_step": int(info_e["d2h"]), "ms_per_step": ms_e, "steps": steps,
                       "api": "gomatching_b200.video.ClipTracker.feed(pinned uint8 HWC frames) -> per-frame track ids on the "
                              "host (frame H2D, frame-batcher kernel, spotter, record gather, reference tracker, ids D2H)"}
+    if world == 1 and not args.no_sublines and not args.verbatim_tracker:
+        # the same loop with GoMatching.run_short_term_match / run_long_term_match called verbatim (identical track ids)
+        ms_v, info_v, _ = run(dev_pool, max(3, steps // 2), clips=1, verbatim=True)
+        res["verbatim_tracker"] = {"value": info_v["per_step"] / (ms_v * 1e-3), "unit": "frames/s", "ms_per_step": ms_v,
+                                   "tracker_ms_per_frame": info_v["assoc_ms_per_frame"],
+                                   "note": "ClipTracker(fast_association=False): the reference's matchers verbatim; same ids"}
     if not args.no_e2e and world == 1 and not args.no_sublines:
         # the same end-to-end loop fed with the frames as JPEG FILES (quality 90, 4:2:0): host Huffman stage in the
         # ClipTracker's decode-ahead threads, IDCT / upsampling / colour conversion on the device (bit-identical to Pillow)
@@ -877,7 +883,7 @@ def main():
                         "the host (track ids bit-identical to the verbatim matchers)"),
             "tracker_ms_per_frame": clip["assoc_ms_per_frame"], "detections_per_frame": clip["detections_per_frame"],
             "score_threshold": clip["score_threshold"], "cuda_graph": clip["graph"], "spotting_only": clip["spotting_only"],
-            "clocks": clocks, "e2e": clip.get("e2e"), "e2e_jpeg": clip.get("e2e_jpeg"), "gpu_launches": clip["launches"],
+            "clocks": clocks, "e2e": clip.get("e2e"), "e2e_jpeg": clip.get("e2e_jpeg"), "verbatim_tracker": clip.get("verbatim_tracker"), "gpu_launches": clip["launches"],
             "gpu_launches_note": "kernel-launching C-ABI calls of libmsda_b200.so in the timed region, all ranks (each "
                                  "enqueues >= 1 kernel); cuDNN / cuBLAS kernels of the reference's eager code not counted",
             "roofline": roofline, "cpu_baseline": cpu, "reference_on_gpu": ref_gpu, "msda": msda, "msda_hbm_gbs": achieved,
