@@ -53,6 +53,33 @@ def round_plan(n_frames: int, weights: Sequence[int]) -> List[List[Tuple[int, in
     return rounds
 
 
+_switch_lock = threading.Lock()
+_switch_users = 0
+_switch_saved: Optional[float] = None
+
+
+def _switch_interval_acquire() -> None:
+    """While any matcher thread lives, CPython's GIL switch interval is 0.5 ms (GOM_SWITCH_INTERVAL seconds; 0 = leave it);
+    the previous value comes back with the last one's ``drain()``."""
+    import os
+    global _switch_users, _switch_saved
+    si = float(os.environ.get("GOM_SWITCH_INTERVAL", "0.0005"))
+    with _switch_lock:
+        _switch_users += 1
+        if _switch_users == 1 and si > 0 and sys.getswitchinterval() > si:
+            _switch_saved = sys.getswitchinterval()
+            sys.setswitchinterval(si)
+
+
+def _switch_interval_release() -> None:
+    global _switch_users, _switch_saved
+    with _switch_lock:
+        _switch_users = max(0, _switch_users - 1)
+        if _switch_users == 0 and _switch_saved is not None:
+            sys.setswitchinterval(_switch_saved)
+            _switch_saved = None
+
+
 class _JpegPrefetch:
     """Decode-ahead for JPEG inputs: the Huffman stage of ``decode_jpeg`` is host work (ctypes releases the GIL), so the
     frames a rank owns are decoded by a few worker threads, each on its own CUDA stream, while the rank spots earlier
@@ -183,10 +210,7 @@ class ClipTracker:
             self._worker.start()
             # two Python threads now share the GIL (spotting + matcher); CPython hands it over only every 5 ms by default,
             # long enough for the replay queue of the spotting thread to run dry.  GOM_SWITCH_INTERVAL (seconds) overrides.
-            import os
-            si = float(os.environ.get("GOM_SWITCH_INTERVAL", "0.0005"))
-            if si > 0 and sys.getswitchinterval() > si:
-                sys.setswitchinterval(si)
+            _switch_interval_acquire()
         shared = model.__dict__.get("_msda_b200_spotter_graph")
         if shared is not None:
             shared.disable()                  # another ClipTracker of this model enabled it: re-point after the batcher below
@@ -404,6 +428,7 @@ class ClipTracker:
             self._worker.join()
             err, self.assoc_worker_s = self._worker.error, self._worker.busy_s
             self._worker = None
+            _switch_interval_release()
             if err is not None:
                 raise err
 

@@ -298,3 +298,16 @@ def test_figure3_known_answer_and_idf1():
     m = acc.summary()
     assert m["num_switches"] == 2 and m["mota"] == pytest.approx(1 - 2 / 16)
     assert m["idtp"] == 8 and m["idf1"] == pytest.approx(0.5)
+
+
+def test_gil_switch_interval_is_lowered_only_while_a_matcher_thread_lives():
+    import sys
+    from gomatching_b200.video import tracking
+    before = sys.getswitchinterval()
+    tracking._switch_interval_acquire()
+    tracking._switch_interval_acquire()
+    assert sys.getswitchinterval() <= min(before, 0.0005) + 1e-12
+    tracking._switch_interval_release()
+    assert sys.getswitchinterval() <= min(before, 0.0005) + 1e-12          # one user left
+    tracking._switch_interval_release()
+    assert abs(sys.getswitchinterval() - before) < 1e-12
